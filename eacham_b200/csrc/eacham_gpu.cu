@@ -1,0 +1,571 @@
+// eacham_gpu.cu -- C ABI (include/eacham_gpu.h) over the sm_100a matching kernels.
+//
+// Host-side runtime for the one hot path of fatlipp/eacham this library replaces: descriptor arena + upload
+// (Node::GetDescriptors feeding Match, /root/reference/apps/sfm/main.cpp:107-108), the reference-shaped
+// single-direction Match (/root/reference/modules/base/features/FeatureMatcherFlann.cpp:14-30) and the batched
+// pair loop (/root/reference/apps/sfm/main.cpp:84-147). No torch types, no exceptions across the boundary,
+// no CPU fallback.
+#include <algorithm>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <new>
+#include <string>
+#include <vector>
+
+#include <cuda_runtime.h>
+
+#include "../../include/eacham_gpu.h"
+#include "l2_kernels.cuh"
+#include "orb_kernels.cuh"
+
+namespace {
+
+thread_local std::string g_last_error;
+
+int fail(int code, const char* fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    g_last_error = buf;
+    return code;
+}
+
+#define CUDA_TRY(expr)                                                                                      \
+    do {                                                                                                    \
+        cudaError_t _e = (expr);                                                                            \
+        if (_e != cudaSuccess)                                                                              \
+            return fail(_e == cudaErrorMemoryAllocation ? EACHAM_ERR_OUT_OF_MEMORY : EACHAM_ERR_CUDA,       \
+                        "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__);        \
+    } while (0)
+
+constexpr size_t kAlign = 128;
+inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+inline size_t row_bytes(int kind) { return kind == EACHAM_KIND_ORB256 ? 32 : 512; }
+
+struct ImageHost {
+    int kind = -1;
+    uint32_t rows = 0;
+    size_t offset = 0;     // byte offset in staging == arena
+    bool present = false;
+    bool has_data = false;
+};
+
+template <typename T>
+struct DevBuf {
+    T* p = nullptr;
+    size_t cap = 0;   // elements
+    int ensure(size_t n) {
+        if (n <= cap) return EACHAM_OK;
+        if (p) cudaFree(p);
+        p = nullptr; cap = 0;
+        size_t want = std::max(n, (size_t)16);
+        cudaError_t e = cudaMalloc(&p, want * sizeof(T));
+        if (e != cudaSuccess) { p = nullptr; return fail(EACHAM_ERR_OUT_OF_MEMORY, "cudaMalloc(%zu bytes) failed: %s", want * sizeof(T), cudaGetErrorString(e)); }
+        cap = want;
+        return EACHAM_OK;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+};
+
+}  // namespace
+
+struct eacham_gpu_handle {
+    int device = 0;
+    int sm_count = 0;
+    size_t smem_optin = 0;
+    cudaStream_t stream = nullptr;
+    std::mutex mu;
+
+    std::vector<ImageHost> images;
+    uint8_t* staging = nullptr;   // pinned
+    size_t staging_cap = 0, staging_used = 0;
+    bool committed = false;
+    bool any_data = false;
+
+    DevBuf<uint8_t> arena;
+    size_t arena_bytes = 0;
+    DevBuf<eacham::orb::ImageDesc> d_images;
+    uint32_t max_rows[2] = {0, 0};
+
+    DevBuf<eacham_pair_t> d_pairs;
+    DevBuf<eacham_pair_result_t> d_results;
+    DevBuf<eacham_match_t> d_matches;
+    DevBuf<uint32_t> d_counter;               // [0] work counter
+    DevBuf<unsigned long long> d_cursor;      // [0] match cursor
+    size_t last_n_pairs = 0;
+    unsigned long long last_total = 0;
+    uint64_t cfg_match_entries = 0;
+
+    // single-pair scratch
+    DevBuf<uint8_t> d_q, d_t;
+    DevBuf<unsigned long long> d_partial;
+    DevBuf<int32_t> d_idx;
+    DevBuf<float> d_dist;
+    DevBuf<uint32_t> d_match, d_match2;
+    DevBuf<uint8_t> d_flush;
+
+    cudaEvent_t ev[8] = {};
+    eacham_gpu_timing timing = {};
+};
+
+namespace {
+
+struct DeviceGuard {
+    int prev = -1;
+    explicit DeviceGuard(int dev) { cudaGetDevice(&prev); if (prev != dev) cudaSetDevice(dev); else prev = -1; }
+    ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+};
+
+int ensure_staging(eacham_gpu_handle* h, size_t need) {
+    if (need <= h->staging_cap) return EACHAM_OK;
+    size_t cap = std::max(need, std::max(h->staging_cap * 2, (size_t)1 << 20));
+    uint8_t* n = nullptr;
+    CUDA_TRY(cudaMallocHost(&n, cap));
+    if (h->staging) { memcpy(n, h->staging, h->staging_used); cudaFreeHost(h->staging); }
+    h->staging = n; h->staging_cap = cap;
+    return EACHAM_OK;
+}
+
+int place_image(eacham_gpu_handle* h, uint32_t image_id, int kind, uint32_t rows, bool& reuse) {
+    if (kind != EACHAM_KIND_ORB256 && kind != EACHAM_KIND_F32X128) return fail(EACHAM_ERR_INVALID_ARG, "unknown descriptor kind %d", kind);
+    if (rows > 65535u) return fail(EACHAM_ERR_TOO_LARGE, "image %u has %u descriptors; at most 65535 are supported", image_id, rows);
+    if (image_id >= h->images.size()) {
+        if (image_id > (1u << 26)) return fail(EACHAM_ERR_INVALID_ARG, "image id %u out of range", image_id);
+        h->images.resize((size_t)image_id + 1);
+    }
+    ImageHost& im = h->images[image_id];
+    reuse = im.present && im.kind == kind && im.rows == rows;
+    if (!reuse) {
+        im.offset = align_up(h->staging_used, kAlign);
+        size_t end = im.offset + (size_t)rows * row_bytes(kind);
+        int rc = ensure_staging(h, align_up(end, kAlign));
+        if (rc) return rc;
+        h->staging_used = end;
+        im.kind = kind; im.rows = rows; im.present = true; im.has_data = false;
+    }
+    h->committed = false;
+    return EACHAM_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int eacham_gpu_abi_version(void) { return EACHAM_GPU_ABI_VERSION; }
+
+const char* eacham_gpu_last_error(void) { return g_last_error.c_str(); }
+
+int eacham_gpu_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+void eacham_gpu_default_opts(eacham_match_opts* o) {
+    if (!o) return;
+    o->ratio = 0.8; o->min_dir = 30; o->min_mutual = 30; o->cross_check = 1; o->emit_all = 0;
+}
+
+int eacham_gpu_create(const eacham_gpu_config* cfg, eacham_gpu_handle** out) {
+    if (!out) return fail(EACHAM_ERR_INVALID_ARG, "out handle pointer is null");
+    *out = nullptr;
+    int dev = cfg ? cfg->device : 0;
+    int n = eacham_gpu_device_count();
+    if (n <= 0) return fail(EACHAM_ERR_NO_DEVICE, "no CUDA device visible; libeacham_gpu has no CPU fallback");
+    if (dev < 0 || dev >= n) return fail(EACHAM_ERR_INVALID_ARG, "device %d out of range (0..%d)", dev, n - 1);
+    cudaDeviceProp prop;
+    CUDA_TRY(cudaGetDeviceProperties(&prop, dev));
+    if (prop.major != 10) return fail(EACHAM_ERR_NO_DEVICE, "device %d is sm_%d%d; this library is built for sm_100a only", dev, prop.major, prop.minor);
+    eacham_gpu_handle* h = new (std::nothrow) eacham_gpu_handle();
+    if (!h) return fail(EACHAM_ERR_OUT_OF_MEMORY, "host allocation failed");
+    h->device = dev;
+    h->sm_count = prop.multiProcessorCount;
+    h->smem_optin = prop.sharedMemPerBlockOptin;
+    h->cfg_match_entries = cfg ? cfg->match_buffer_entries : 0;
+    DeviceGuard g(dev);
+    cudaError_t e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking);
+    for (int i = 0; i < 8 && e == cudaSuccess; ++i) e = cudaEventCreate(&h->ev[i]);
+    if (e != cudaSuccess) { delete h; return fail(EACHAM_ERR_CUDA, "stream/event creation failed: %s", cudaGetErrorString(e)); }
+    if (h->d_counter.ensure(16) || h->d_cursor.ensure(16)) { delete h; return EACHAM_ERR_OUT_OF_MEMORY; }
+    *out = h;
+    return EACHAM_OK;
+}
+
+void eacham_gpu_destroy(eacham_gpu_handle* h) {
+    if (!h) return;
+    {
+        DeviceGuard g(h->device);
+        cudaStreamSynchronize(h->stream);
+        h->arena.release(); h->d_images.release(); h->d_pairs.release(); h->d_results.release(); h->d_matches.release();
+        h->d_counter.release(); h->d_cursor.release(); h->d_q.release(); h->d_t.release(); h->d_partial.release();
+        h->d_idx.release(); h->d_dist.release(); h->d_match.release(); h->d_match2.release(); h->d_flush.release();
+        if (h->staging) cudaFreeHost(h->staging);
+        for (auto& e : h->ev) if (e) cudaEventDestroy(e);
+        if (h->stream) cudaStreamDestroy(h->stream);
+    }
+    delete h;
+}
+
+int eacham_gpu_set_descriptors(eacham_gpu_handle* h, uint32_t image_id, int kind, const void* data, uint32_t rows,
+                               size_t row_stride_bytes) {
+    if (!h) return fail(EACHAM_ERR_INVALID_ARG, "null handle");
+    if (rows > 0 && !data) return fail(EACHAM_ERR_INVALID_ARG, "null descriptor pointer for image %u", image_id);
+    std::lock_guard<std::mutex> lk(h->mu);
+    DeviceGuard g(h->device);
+    bool reuse = false;
+    int rc = place_image(h, image_id, kind, rows, reuse);
+    if (rc) return rc;
+    const size_t rb = row_bytes(kind);
+    if (rows > 0 && row_stride_bytes < rb) return fail(EACHAM_ERR_INVALID_ARG, "row stride %zu < row size %zu", row_stride_bytes, rb);
+    ImageHost& im = h->images[image_id];
+    uint8_t* dst = h->staging + im.offset;
+    if (row_stride_bytes == rb) memcpy(dst, data, (size_t)rows * rb);
+    else for (uint32_t r = 0; r < rows; ++r) memcpy(dst + (size_t)r * rb, (const uint8_t*)data + (size_t)r * row_stride_bytes, rb);
+    im.has_data = true;
+    h->any_data = true;
+    return EACHAM_OK;
+}
+
+int eacham_gpu_reserve(eacham_gpu_handle* h, uint32_t image_id, int kind, uint32_t rows) {
+    if (!h) return fail(EACHAM_ERR_INVALID_ARG, "null handle");
+    std::lock_guard<std::mutex> lk(h->mu);
+    DeviceGuard g(h->device);
+    bool reuse = false;
+    return place_image(h, image_id, kind, rows, reuse);
+}
+
+int eacham_gpu_clear(eacham_gpu_handle* h) {
+    if (!h) return fail(EACHAM_ERR_INVALID_ARG, "null handle");
+    std::lock_guard<std::mutex> lk(h->mu);
+    h->images.clear();
+    h->staging_used = 0; h->committed = false; h->any_data = false; h->arena_bytes = 0;
+    h->max_rows[0] = h->max_rows[1] = 0;
+    return EACHAM_OK;
+}
+
+int eacham_gpu_commit(eacham_gpu_handle* h) {
+    if (!h) return fail(EACHAM_ERR_INVALID_ARG, "null handle");
+    std::lock_guard<std::mutex> lk(h->mu);
+    DeviceGuard g(h->device);
+    const size_t bytes = align_up(std::max(h->staging_used, (size_t)1), kAlign);
+    int rc = h->arena.ensure(bytes + kAlign);
+    if (rc) return rc;
+    if ((rc = h->d_images.ensure(std::max(h->images.size(), (size_t)1)))) return rc;
+    std::vector<eacham::orb::ImageDesc> table(h->images.size());
+    h->max_rows[0] = h->max_rows[1] = 0;
+    for (size_t i = 0; i < h->images.size(); ++i) {
+        const ImageHost& im = h->images[i];
+        table[i].offset = im.offset;
+        table[i].rows = im.present ? im.rows : 0;
+        table[i].kind = im.present ? (uint32_t)im.kind : 0xffffffffu;
+        if (im.present) h->max_rows[im.kind] = std::max(h->max_rows[im.kind], im.rows);
+    }
+    CUDA_TRY(cudaEventRecord(h->ev[0], h->stream));
+    if (h->any_data && h->staging_used > 0)
+        CUDA_TRY(cudaMemcpyAsync(h->arena.p, h->staging, h->staging_used, cudaMemcpyHostToDevice, h->stream));
+    if (!table.empty())
+        CUDA_TRY(cudaMemcpyAsync(h->d_images.p, table.data(), table.size() * sizeof(table[0]), cudaMemcpyHostToDevice, h->stream));
+    CUDA_TRY(cudaEventRecord(h->ev[1], h->stream));
+    CUDA_TRY(cudaStreamSynchronize(h->stream));
+    CUDA_TRY(cudaEventElapsedTime(&h->timing.upload_ms, h->ev[0], h->ev[1]));
+    h->arena_bytes = bytes;
+    h->committed = true;
+    return EACHAM_OK;
+}
+
+int eacham_gpu_arena(eacham_gpu_handle* h, void** device_ptr, size_t* bytes) {
+    if (!h) return fail(EACHAM_ERR_INVALID_ARG, "null handle");
+    std::lock_guard<std::mutex> lk(h->mu);
+    if (!h->committed) return fail(EACHAM_ERR_NOT_COMMITTED, "arena queried before eacham_gpu_commit");
+    if (device_ptr) *device_ptr = h->arena.p;
+    if (bytes) *bytes = h->arena_bytes;
+    return EACHAM_OK;
+}
+
+int eacham_gpu_image_info(eacham_gpu_handle* h, uint32_t image_id, int* kind, uint32_t* rows, size_t* arena_offset) {
+    if (!h) return fail(EACHAM_ERR_INVALID_ARG, "null handle");
+    std::lock_guard<std::mutex> lk(h->mu);
+    if (image_id >= h->images.size() || !h->images[image_id].present) return fail(EACHAM_ERR_INVALID_ARG, "image %u has no descriptors", image_id);
+    const ImageHost& im = h->images[image_id];
+    if (kind) *kind = im.kind;
+    if (rows) *rows = im.rows;
+    if (arena_offset) *arena_offset = im.offset;
+    return EACHAM_OK;
+}
+
+int eacham_gpu_last_timing(eacham_gpu_handle* h, eacham_gpu_timing* t) {
+    if (!h || !t) return fail(EACHAM_ERR_INVALID_ARG, "null argument");
+    std::lock_guard<std::mutex> lk(h->mu);
+    *t = h->timing;
+    return EACHAM_OK;
+}
+
+int eacham_gpu_flush_l2(eacham_gpu_handle* h, size_t bytes) {
+    if (!h) return fail(EACHAM_ERR_INVALID_ARG, "null handle");
+    std::lock_guard<std::mutex> lk(h->mu);
+    DeviceGuard g(h->device);
+    int rc = h->d_flush.ensure(bytes);
+    if (rc) return rc;
+    CUDA_TRY(cudaMemsetAsync(h->d_flush.p, 0x5a, bytes, h->stream));
+    CUDA_TRY(cudaStreamSynchronize(h->stream));
+    return EACHAM_OK;
+}
+
+}  // extern "C"
+
+// -------------------------------------------------------------------------------------------------------------
+// single pair, single direction
+// -------------------------------------------------------------------------------------------------------------
+namespace {
+
+// kNN-2 of q (device, nq rows) in t (device, nt rows); outputs on device. Any of idx/dist, match may be null.
+int knn2_device(eacham_gpu_handle* h, int kind, const void* dq, uint32_t nq, const void* dt, uint32_t nt, double ratio,
+                int32_t* d_idx, float* d_dist, uint32_t* d_match, uint32_t* launches) {
+    if (nq == 0) return EACHAM_OK;
+    using namespace eacham;
+    if (kind == EACHAM_KIND_ORB256) {
+        const uint32_t row_blocks = (nq + orb::kKnnRowBlock - 1) / orb::kKnnRowBlock;
+        uint32_t want = std::max(1u, (uint32_t)(2 * h->sm_count) / row_blocks);
+        uint32_t tiles = std::max(1u, (nt + orb::kKnnTile - 1) / orb::kKnnTile);
+        uint32_t nsplit = std::min(want, tiles);
+        uint32_t cols_per_split = ((tiles + nsplit - 1) / nsplit) * orb::kKnnTile;
+        nsplit = std::max(1u, (nt + cols_per_split - 1) / cols_per_split);
+        int rc = h->d_partial.ensure((size_t)nsplit * nq);
+        if (rc) return rc;
+        orb::orb_knn2_partial_kernel<<<dim3(row_blocks, nsplit), orb::kKnnThreads, 0, h->stream>>>(
+            (const uint8_t*)dq, nq, (const uint8_t*)dt, nt, cols_per_split, (uint2*)h->d_partial.p);
+        orb::orb_knn2_finalize_kernel<<<(nq + 255) / 256, 256, 0, h->stream>>>((const uint2*)h->d_partial.p, nq, nsplit, ratio,
+                                                                                d_idx, d_dist, d_match);
+    } else {
+        const uint32_t row_blocks = (nq + l2::kBM - 1) / l2::kBM;
+        uint32_t want = std::max(1u, (uint32_t)(2 * h->sm_count) / row_blocks);
+        uint32_t tiles = std::max(1u, (nt + l2::kBN - 1) / l2::kBN);
+        uint32_t nsplit = std::min(want, tiles);
+        uint32_t cols_per_split = ((tiles + nsplit - 1) / nsplit) * l2::kBN;
+        nsplit = std::max(1u, (nt + cols_per_split - 1) / cols_per_split);
+        int rc = h->d_partial.ensure((size_t)nsplit * nq * 2);
+        if (rc) return rc;
+        l2::l2_knn2_partial_kernel<<<dim3(row_blocks, nsplit), l2::kThreads, 0, h->stream>>>(
+            (const float*)dq, nq, (const float*)dt, nt, cols_per_split, h->d_partial.p);
+        l2::l2_knn2_finalize_kernel<<<(nq + 255) / 256, 256, 0, h->stream>>>(h->d_partial.p, nq, nsplit, ratio, d_idx, d_dist,
+                                                                              d_match);
+    }
+    if (launches) *launches += 2;
+    CUDA_TRY(cudaGetLastError());
+    return EACHAM_OK;
+}
+
+int upload_rows(eacham_gpu_handle* h, DevBuf<uint8_t>& dst, int kind, const void* src, uint32_t rows, size_t stride) {
+    const size_t rb = row_bytes(kind);
+    int rc = dst.ensure(std::max((size_t)rows * rb, (size_t)rb));
+    if (rc) return rc;
+    if (rows == 0) return EACHAM_OK;
+    if (stride < rb) return fail(EACHAM_ERR_INVALID_ARG, "row stride %zu < row size %zu", stride, rb);
+    CUDA_TRY(cudaMemcpy2DAsync(dst.p, rb, src, stride, rb, rows, cudaMemcpyHostToDevice, h->stream));
+    return EACHAM_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int eacham_gpu_knn2(eacham_gpu_handle* h, int kind, const void* query, uint32_t q_rows, size_t q_stride,
+                    const void* train, uint32_t t_rows, size_t t_stride, int32_t* idx, float* dist) {
+    if (!h) return fail(EACHAM_ERR_INVALID_ARG, "null handle");
+    if (kind != EACHAM_KIND_ORB256 && kind != EACHAM_KIND_F32X128) return fail(EACHAM_ERR_INVALID_ARG, "unknown descriptor kind %d", kind);
+    if ((q_rows && !query) || (t_rows && !train) || (q_rows && (!idx || !dist))) return fail(EACHAM_ERR_INVALID_ARG, "null pointer argument");
+    if (q_rows > 65535u || t_rows > 65535u) return fail(EACHAM_ERR_TOO_LARGE, "at most 65535 descriptors per image");
+    if (q_rows == 0) return EACHAM_OK;
+    std::lock_guard<std::mutex> lk(h->mu);
+    DeviceGuard g(h->device);
+    int rc;
+    if ((rc = upload_rows(h, h->d_q, kind, query, q_rows, q_stride))) return rc;
+    if ((rc = upload_rows(h, h->d_t, kind, train, t_rows, t_stride))) return rc;
+    if ((rc = h->d_idx.ensure((size_t)q_rows * 2))) return rc;
+    if ((rc = h->d_dist.ensure((size_t)q_rows * 2))) return rc;
+    if ((rc = knn2_device(h, kind, h->d_q.p, q_rows, h->d_t.p, t_rows, 0.8, h->d_idx.p, h->d_dist.p, nullptr, nullptr))) return rc;
+    CUDA_TRY(cudaMemcpyAsync(idx, h->d_idx.p, (size_t)q_rows * 2 * sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(cudaMemcpyAsync(dist, h->d_dist.p, (size_t)q_rows * 2 * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(cudaStreamSynchronize(h->stream));
+    return EACHAM_OK;
+}
+
+int eacham_gpu_match(eacham_gpu_handle* h, int kind, const void* query, uint32_t q_rows, size_t q_stride,
+                     const void* train, uint32_t t_rows, size_t t_stride, double ratio, eacham_match_t* out, size_t cap,
+                     size_t* n_out) {
+    if (!h) return fail(EACHAM_ERR_INVALID_ARG, "null handle");
+    if (kind != EACHAM_KIND_ORB256 && kind != EACHAM_KIND_F32X128) return fail(EACHAM_ERR_INVALID_ARG, "unknown descriptor kind %d", kind);
+    if ((q_rows && !query) || (t_rows && !train) || !n_out || (cap && !out)) return fail(EACHAM_ERR_INVALID_ARG, "null pointer argument");
+    if (q_rows > 65535u || t_rows > 65535u) return fail(EACHAM_ERR_TOO_LARGE, "at most 65535 descriptors per image");
+    *n_out = 0;
+    if (q_rows == 0 || t_rows == 0) return EACHAM_OK;
+    std::lock_guard<std::mutex> lk(h->mu);
+    DeviceGuard g(h->device);
+    int rc;
+    if ((rc = upload_rows(h, h->d_q, kind, query, q_rows, q_stride))) return rc;
+    if ((rc = upload_rows(h, h->d_t, kind, train, t_rows, t_stride))) return rc;
+    if ((rc = h->d_match.ensure(q_rows))) return rc;
+    if ((rc = knn2_device(h, kind, h->d_q.p, q_rows, h->d_t.p, t_rows, ratio, nullptr, nullptr, h->d_match.p, nullptr))) return rc;
+    std::vector<uint32_t> m(q_rows);
+    CUDA_TRY(cudaMemcpyAsync(m.data(), h->d_match.p, (size_t)q_rows * sizeof(uint32_t), cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(cudaStreamSynchronize(h->stream));
+    size_t n = 0;
+    for (uint32_t i = 0; i < q_rows; ++i)
+        if (m[i] != EACHAM_NONE) {
+            if (n < cap) { out[n].query = i; out[n].train = m[i]; }
+            ++n;
+        }
+    *n_out = n;
+    if (n > cap) return fail(EACHAM_ERR_BUFFER_TOO_SMALL, "match buffer holds %zu entries, %zu needed", cap, n);
+    return EACHAM_OK;
+}
+
+}  // extern "C"
+
+// -------------------------------------------------------------------------------------------------------------
+// batched pairs
+// -------------------------------------------------------------------------------------------------------------
+namespace {
+
+int launch_pairs(eacham_gpu_handle* h, const eacham_pair_t* pairs, size_t n_pairs, const eacham_match_opts* opts_in) {
+    using namespace eacham;
+    if (!h->committed) return fail(EACHAM_ERR_NOT_COMMITTED, "eacham_gpu_match_pairs called before eacham_gpu_commit");
+    if (n_pairs > 0xfffffff0ull) return fail(EACHAM_ERR_INVALID_ARG, "too many pairs");
+    eacham_match_opts o;
+    if (opts_in) o = *opts_in; else eacham_gpu_default_opts(&o);
+    h->timing.kernel_launches = 0;
+    h->timing.kernel_ms = h->timing.pairs_h2d_ms = h->timing.d2h_ms = 0.f;
+    h->last_n_pairs = n_pairs;
+    h->last_total = 0;
+    if (n_pairs == 0) return EACHAM_OK;
+
+    // validate the pair list against the image table; all pairs of a call share one descriptor kind
+    int kind = -1;
+    uint32_t max_first = 0, max_second = 0;
+    for (size_t i = 0; i < n_pairs; ++i) {
+        const uint32_t a = pairs[i].first, b = pairs[i].second;
+        if (a >= h->images.size() || b >= h->images.size() || !h->images[a].present || !h->images[b].present)
+            return fail(EACHAM_ERR_NOT_COMMITTED, "pair %zu = (%u, %u) names an image without descriptors", i, a, b);
+        if (kind < 0) kind = h->images[a].kind;
+        if (h->images[a].kind != kind || h->images[b].kind != kind)
+            return fail(EACHAM_ERR_KIND_MISMATCH, "pair %zu = (%u, %u) mixes descriptor kinds", i, a, b);
+        max_first = std::max(max_first, h->images[a].rows);
+        max_second = std::max(max_second, h->images[b].rows);
+    }
+
+    int rc;
+    if ((rc = h->d_pairs.ensure(n_pairs))) return rc;
+    if ((rc = h->d_results.ensure(n_pairs))) return rc;
+    size_t want_entries = h->cfg_match_entries ? (size_t)h->cfg_match_entries
+                                               : std::max((size_t)1 << 20, n_pairs * (size_t)192);
+    if (h->d_matches.cap < want_entries && (rc = h->d_matches.ensure(want_entries))) return rc;
+
+    CUDA_TRY(cudaEventRecord(h->ev[2], h->stream));
+    CUDA_TRY(cudaMemcpyAsync(h->d_pairs.p, pairs, n_pairs * sizeof(eacham_pair_t), cudaMemcpyHostToDevice, h->stream));
+    CUDA_TRY(cudaEventRecord(h->ev[3], h->stream));
+
+    for (int attempt = 0; attempt < 2; ++attempt) {
+        CUDA_TRY(cudaMemsetAsync(h->d_counter.p, 0, sizeof(uint32_t), h->stream));
+        CUDA_TRY(cudaMemsetAsync(h->d_cursor.p, 0, sizeof(unsigned long long), h->stream));
+        CUDA_TRY(cudaEventRecord(h->ev[4], h->stream));
+        if (kind == EACHAM_KIND_ORB256 && max_first <= orb::kMaxRowsFused && max_second <= orb::kMaxRowsFused) {
+            orb::PairParams p;
+            p.arena = h->arena.p; p.images = h->d_images.p; p.pairs = h->d_pairs.p; p.n_pairs = (uint32_t)n_pairs;
+            p.work_counter = h->d_counter.p;
+            p.ratio = o.ratio; p.min_dir = o.min_dir; p.min_mutual = o.min_mutual; p.cross_check = o.cross_check; p.emit_all = o.emit_all;
+            p.results = h->d_results.p; p.matches = h->d_matches.p; p.matches_cap = h->d_matches.cap; p.cursor = h->d_cursor.p;
+            p.smem_cols = (uint32_t)align_up(std::max(max_second, 4u), 4);
+            p.smem_rows = (uint32_t)align_up(std::max(max_first, 8u), 8);
+            const size_t smem = orb::pair_smem_bytes(p.smem_cols, p.smem_rows);
+            if (smem > h->smem_optin) return fail(EACHAM_ERR_TOO_LARGE, "pair kernel needs %zu bytes of shared memory (> %zu)", smem, h->smem_optin);
+            CUDA_TRY(cudaFuncSetAttribute(orb::orb_match_pairs_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            const unsigned grid = (unsigned)std::min<size_t>(n_pairs, (size_t)h->sm_count);
+            orb::orb_match_pairs_kernel<<<grid, orb::kThreads, smem, h->stream>>>(p);
+            CUDA_TRY(cudaGetLastError());
+            h->timing.kernel_launches += 1;
+        } else {
+            // exact per-pair path: two kNN directions + finalisation (SIFT FP32; ORB images beyond the fused limit)
+            const uint32_t max_rows = std::max(max_first, max_second);
+            if ((rc = h->d_match.ensure(max_rows)) || (rc = h->d_match2.ensure(max_rows))) return rc;
+            for (size_t i = 0; i < n_pairs; ++i) {
+                const ImageHost& A = h->images[pairs[i].first];
+                const ImageHost& B = h->images[pairs[i].second];
+                if (A.rows && (rc = knn2_device(h, kind, h->arena.p + A.offset, A.rows, h->arena.p + B.offset, B.rows, o.ratio, nullptr,
+                                                nullptr, h->d_match.p, &h->timing.kernel_launches))) return rc;
+                if (B.rows && (rc = knn2_device(h, kind, h->arena.p + B.offset, B.rows, h->arena.p + A.offset, A.rows, o.ratio, nullptr,
+                                                nullptr, h->d_match2.p, &h->timing.kernel_launches))) return rc;
+                FinalizeParams f;
+                f.m12 = h->d_match.p; f.n1 = A.rows; f.m21 = h->d_match2.p; f.n2 = B.rows;
+                f.min_dir = o.min_dir; f.min_mutual = o.min_mutual; f.cross_check = o.cross_check; f.emit_all = o.emit_all;
+                f.result = h->d_results.p + i; f.matches = h->d_matches.p; f.matches_cap = h->d_matches.cap; f.cursor = h->d_cursor.p;
+                pair_finalize_kernel<<<1, 256, 0, h->stream>>>(f);
+                h->timing.kernel_launches += 1;
+            }
+            CUDA_TRY(cudaGetLastError());
+        }
+        CUDA_TRY(cudaEventRecord(h->ev[5], h->stream));
+        unsigned long long used = 0;
+        CUDA_TRY(cudaMemcpyAsync(&used, h->d_cursor.p, sizeof(used), cudaMemcpyDeviceToHost, h->stream));
+        CUDA_TRY(cudaStreamSynchronize(h->stream));
+        h->last_total = used;
+        if (used <= h->d_matches.cap) break;
+        if (attempt == 1) return fail(EACHAM_ERR_OUT_OF_MEMORY, "match buffer overflow persisted after regrow");
+        if ((rc = h->d_matches.ensure((size_t)used + 1024))) return rc;   // deterministic need: rerun once
+    }
+    CUDA_TRY(cudaEventElapsedTime(&h->timing.pairs_h2d_ms, h->ev[2], h->ev[3]));
+    CUDA_TRY(cudaEventElapsedTime(&h->timing.kernel_ms, h->ev[4], h->ev[5]));
+    return EACHAM_OK;
+}
+
+int fetch(eacham_gpu_handle* h, eacham_pair_result_t* res, size_t n_pairs, eacham_match_t* buf, size_t buf_cap, size_t* buf_used) {
+    if (n_pairs != h->last_n_pairs) return fail(EACHAM_ERR_INVALID_ARG, "fetch of %zu pairs but the last batch had %zu", n_pairs, h->last_n_pairs);
+    if (buf_used) *buf_used = (size_t)h->last_total;
+    if (n_pairs == 0) return EACHAM_OK;
+    CUDA_TRY(cudaEventRecord(h->ev[6], h->stream));
+    if (res) CUDA_TRY(cudaMemcpyAsync(res, h->d_results.p, n_pairs * sizeof(eacham_pair_result_t), cudaMemcpyDeviceToHost, h->stream));
+    const size_t n_copy = std::min((size_t)h->last_total, buf_cap);
+    if (buf && n_copy) CUDA_TRY(cudaMemcpyAsync(buf, h->d_matches.p, n_copy * sizeof(eacham_match_t), cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(cudaEventRecord(h->ev[7], h->stream));
+    CUDA_TRY(cudaStreamSynchronize(h->stream));
+    CUDA_TRY(cudaEventElapsedTime(&h->timing.d2h_ms, h->ev[6], h->ev[7]));
+    if (h->last_total > buf_cap) return fail(EACHAM_ERR_BUFFER_TOO_SMALL, "match buffer holds %zu entries, %llu needed", buf_cap, h->last_total);
+    return EACHAM_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int eacham_gpu_match_pairs_device(eacham_gpu_handle* h, const eacham_pair_t* pairs, size_t n_pairs,
+                                  const eacham_match_opts* opts, size_t* total_matches) {
+    if (!h || (n_pairs && !pairs)) return fail(EACHAM_ERR_INVALID_ARG, "null argument");
+    std::lock_guard<std::mutex> lk(h->mu);
+    DeviceGuard g(h->device);
+    int rc = launch_pairs(h, pairs, n_pairs, opts);
+    if (total_matches) *total_matches = (size_t)h->last_total;
+    return rc;
+}
+
+int eacham_gpu_fetch_results(eacham_gpu_handle* h, eacham_pair_result_t* res, size_t n_pairs, eacham_match_t* buf,
+                             size_t buf_cap, size_t* buf_used) {
+    if (!h) return fail(EACHAM_ERR_INVALID_ARG, "null handle");
+    std::lock_guard<std::mutex> lk(h->mu);
+    DeviceGuard g(h->device);
+    return fetch(h, res, n_pairs, buf, buf_cap, buf_used);
+}
+
+int eacham_gpu_match_pairs(eacham_gpu_handle* h, const eacham_pair_t* pairs, size_t n_pairs, const eacham_match_opts* opts,
+                           eacham_pair_result_t* res, eacham_match_t* buf, size_t buf_cap, size_t* buf_used) {
+    if (!h || (n_pairs && (!pairs || !res)) || (buf_cap && !buf)) return fail(EACHAM_ERR_INVALID_ARG, "null argument");
+    std::lock_guard<std::mutex> lk(h->mu);
+    DeviceGuard g(h->device);
+    int rc = launch_pairs(h, pairs, n_pairs, opts);
+    if (rc) return rc;
+    return fetch(h, res, n_pairs, buf, buf_cap, buf_used);
+}
+
+}  // extern "C"

@@ -1,0 +1,120 @@
+"""Multi-GPU plumbing: one process per GPU, torch.distributed (NCCL over NVLink/NVSwitch) for the two
+collectives the path has -- nothing on the data path itself.
+
+The pair list of /root/reference/apps/sfm/main.cpp:84-92 is a set of independent units, so it shards with no
+exchange step: every rank holds the whole descriptor arena (262 MB for 2,000 x 4k ORB -- trivial next to 180 GB of
+HBM3e), matches ``pairs[rank::world]`` and keeps its results. The collectives are
+  * one broadcast of the arena bytes from the rank that owns the host descriptors, and
+  * an optional gather of the per-pair results to one rank.
+torch is used only to move bytes; the arena memory belongs to libeacham_gpu.so on every rank.
+"""
+from __future__ import annotations
+
+from typing import List, Optional, Sequence, Tuple
+
+import numpy as np
+
+from . import _lib as L
+
+
+def shard_pairs(pairs: np.ndarray, rank: int, world: int) -> np.ndarray:
+    """Rank r takes pairs r, r+world, r+2*world, ... -- equal counts (+-1) and, for an exhaustive list in
+    row-major order, an even mix of images on every rank."""
+    return np.ascontiguousarray(np.asarray(pairs, dtype=np.uint32).reshape(-1, 2)[rank::world])
+
+
+def shard_sizes(n_pairs: int, world: int) -> List[int]:
+    return [len(range(r, n_pairs, world)) for r in range(world)]
+
+
+def unshard(per_rank: Sequence[np.ndarray], n_pairs: int) -> np.ndarray:
+    """Inverse of shard_pairs for per-pair arrays: per_rank[r][k] belongs to pair r + k*world."""
+    world = len(per_rank)
+    out = np.empty((n_pairs,) + per_rank[0].shape[1:], dtype=per_rank[0].dtype)
+    for r in range(world):
+        out[r::world] = per_rank[r]
+    return out
+
+
+class _CudaBytes:
+    """A raw device range exposed through __cuda_array_interface__ so torch can address library-owned memory."""
+
+    def __init__(self, ptr: int, nbytes: int):
+        self.__cuda_array_interface__ = {"shape": (nbytes,), "typestr": "|u1", "data": (ptr, False), "version": 3,
+                                         "strides": None}
+
+
+def arena_tensor(matcher):
+    """uint8 CUDA tensor aliasing the matcher's committed device arena (no copy)."""
+    import torch
+    ptr, nbytes = matcher.arena()
+    return torch.as_tensor(_CudaBytes(ptr, nbytes), device=f"cuda:{matcher.device}")
+
+
+def upload_and_broadcast(matcher, descriptors: Optional[Sequence[np.ndarray]], src: int = 0, group=None) -> int:
+    """Every rank lays out the same arena; ``src`` uploads the bytes (one H2D) and broadcasts them once over NCCL.
+    ``descriptors`` is needed on ``src`` only. Returns the arena size in bytes."""
+    import torch
+    import torch.distributed as dist
+    rank = dist.get_rank(group)
+    if rank == src:
+        shapes = [(0 if d.dtype == np.uint8 else 1, int(d.shape[0])) for d in descriptors]
+    else:
+        shapes = None
+    box = [shapes]
+    dist.broadcast_object_list(box, src=src, group=group)
+    shapes = box[0]
+    matcher.Clear()
+    for i, (kind, rows) in enumerate(shapes):
+        if rank == src:
+            matcher.SetDescriptors(i, descriptors[i])
+        else:
+            matcher.Reserve(i, kind, rows)
+    matcher.Commit()
+    t = arena_tensor(matcher)
+    dist.broadcast(t, src=src, group=group)
+    torch.cuda.synchronize(matcher.device)
+    return int(t.numel())
+
+
+def gather_results(res: np.ndarray, matches: np.ndarray, n_pairs_total: int, dst: int = 0, group=None,
+                   device: Optional[str] = None) -> Optional[Tuple[np.ndarray, np.ndarray]]:
+    """Gathers each rank's (results, matches) record arrays onto ``dst`` and restores the original pair order.
+    Offsets are rebased into the concatenated match buffer. Works on gloo (CPU tensors) and nccl (CUDA tensors).
+    Returns (results[n_pairs_total], matches[total]) on dst, None elsewhere."""
+    import torch
+    import torch.distributed as dist
+    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    dev = device or ("cuda" if dist.get_backend(group) == "nccl" else "cpu")
+    sizes = torch.tensor([res.shape[0], matches.shape[0]], dtype=torch.int64, device=dev)
+    all_sizes = [torch.zeros(2, dtype=torch.int64, device=dev) for _ in range(world)]
+    dist.all_gather(all_sizes, sizes, group=group)
+    all_sizes = [s.cpu().tolist() for s in all_sizes]
+    max_r = max(s[0] for s in all_sizes); max_m = max(s[1] for s in all_sizes)
+
+    def padded(arr: np.ndarray, itemsize: int, n_max: int):
+        raw = np.zeros(max(n_max, 1) * itemsize, np.uint8)
+        b = arr.view(np.uint8).reshape(-1)
+        raw[:b.shape[0]] = b
+        return torch.from_numpy(raw).to(dev)
+
+    tr = padded(res, np.dtype(L.RESULT_DTYPE).itemsize, max_r)
+    tm = padded(matches, np.dtype(L.MATCH_DTYPE).itemsize, max_m)
+    if rank == dst:
+        gr = [torch.empty_like(tr) for _ in range(world)]
+        gm = [torch.empty_like(tm) for _ in range(world)]
+    else:
+        gr = gm = None
+    dist.gather(tr, gr, dst=dst, group=group)
+    dist.gather(tm, gm, dst=dst, group=group)
+    if rank != dst:
+        return None
+    per_res, per_m, base = [], [], 0
+    for r in range(world):
+        nr, nm = all_sizes[r]
+        rr = gr[r].cpu().numpy()[: nr * np.dtype(L.RESULT_DTYPE).itemsize].view(L.RESULT_DTYPE).copy()
+        mm = gm[r].cpu().numpy()[: nm * np.dtype(L.MATCH_DTYPE).itemsize].view(L.MATCH_DTYPE).copy()
+        rr["offset"] += base
+        base += nm
+        per_res.append(rr); per_m.append(mm)
+    return unshard(per_res, n_pairs_total), np.concatenate(per_m) if per_m else np.zeros(0, L.MATCH_DTYPE)

@@ -1,0 +1,169 @@
+/*
+ * eacham_gpu.h -- C ABI of the B200-native descriptor matcher (libeacham_gpu.so).
+ *
+ * This is the drop-in boundary for ONE path of fatlipp/eacham: the all-pairs descriptor matching phase.
+ * Every entry point names the reference interface it replaces (paths relative to the reference root):
+ *
+ *   eacham_gpu_match        <- FeatureMatcherFlann::Match      modules/base/features/FeatureMatcherFlann.cpp:14-30
+ *                              (IFeatureMatcher<T>::Match       modules/base/features/IFeatureMatcher.h:18-19)
+ *   eacham_gpu_match_pairs  <- the pair loop + cross-check      apps/sfm/main.cpp:84-147
+ *   eacham_gpu_set_descriptors / eacham_gpu_commit
+ *                           <- Node::GetDescriptors() feeding Match   modules/sfm/data/Node.h:136-139, apps/sfm/main.cpp:107-108
+ *   eacham_match_t          <- one entry of match_t              modules/sfm/data/Types.h:34
+ *
+ * Conventions: plain pointers and sizes only; no allocation crosses the ABI (outputs go into caller buffers with
+ * capacity in / count out); every function returns an eacham_status (0 = ok, <0 = error) and never throws;
+ * eacham_gpu_last_error() returns a thread-local message for the last failure on the calling thread.
+ * There is NO CPU fallback: without a usable CUDA device eacham_gpu_create fails with EACHAM_ERR_NO_DEVICE.
+ *
+ * Thread-safety: a handle may be used from several threads at once (the reference calls Match concurrently on one
+ * matcher object from TBB workers, apps/sfm/main.cpp:98-109); calls on one handle are serialised internally.
+ */
+#ifndef EACHAM_GPU_H
+#define EACHAM_GPU_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define EACHAM_GPU_ABI_VERSION 1
+
+#if defined(__GNUC__)
+#define EACHAM_API __attribute__((visibility("default")))
+#else
+#define EACHAM_API
+#endif
+
+typedef enum eacham_status {
+    EACHAM_OK = 0,
+    EACHAM_ERR_INVALID_ARG = -1,
+    EACHAM_ERR_NO_DEVICE = -2,      /* no CUDA device / wrong architecture: there is no CPU fallback          */
+    EACHAM_ERR_CUDA = -3,           /* a CUDA runtime call failed; see eacham_gpu_last_error()                 */
+    EACHAM_ERR_OUT_OF_MEMORY = -4,
+    EACHAM_ERR_BUFFER_TOO_SMALL = -5, /* caller buffer too small; the required count is reported back           */
+    EACHAM_ERR_NOT_COMMITTED = -6,  /* match_pairs before commit, or an image id without descriptors            */
+    EACHAM_ERR_TOO_LARGE = -7,      /* more descriptors per image than the kernels support (65535)              */
+    EACHAM_ERR_KIND_MISMATCH = -8   /* a pair mixes ORB and SIFT images                                          */
+} eacham_status;
+
+/* Descriptor kinds. ORB256: rows of 32 bytes (8 x int32, modules/base/tools/Tools3d.h:46-63), Hamming distance.
+ * F32X128: rows of 128 float32 (cv::SIFT output, modules/base/features/FeatureExtractorSift.cpp:14-26), L2.  */
+typedef enum eacham_kind {
+    EACHAM_KIND_ORB256 = 0,
+    EACHAM_KIND_F32X128 = 1
+} eacham_kind;
+
+#define EACHAM_NONE 0xFFFFFFFFu
+
+typedef struct eacham_gpu_handle eacham_gpu_handle;
+
+typedef struct eacham_gpu_config {
+    int32_t device;               /* CUDA device ordinal                                                     */
+    uint32_t max_images;          /* 0 = grow on demand                                                      */
+    uint64_t match_buffer_entries;/* device-side capacity for compacted matches; 0 = sized per call          */
+    uint32_t flags;               /* reserved, must be 0                                                     */
+} eacham_gpu_config;
+
+/* {queryIdx -> trainIdx}: one entry of the reference's std::unordered_map<unsigned, unsigned>. */
+typedef struct eacham_match_t {
+    uint32_t query;
+    uint32_t train;
+} eacham_match_t;
+
+/* An unordered image pair {first, second}; the reference enumerates both ordered pairs (main.cpp:84-92) and
+ * recomputes the transposed distance matrix; here one entry covers both directions. */
+typedef struct eacham_pair_t {
+    uint32_t first;
+    uint32_t second;
+} eacham_pair_t;
+
+typedef struct eacham_match_opts {
+    double ratio;         /* Lowe ratio; the reference hard-codes the double literal 0.8 (FeatureMatcherFlann.cpp:23) */
+    uint32_t min_dir;     /* per-direction gate: drop the pair if a direction has < min_dir matches (main.cpp:111) = 30 */
+    uint32_t min_mutual;  /* connect iff mutual count > min_mutual (main.cpp:142, strict)                    = 30 */
+    uint32_t cross_check; /* 1 = mutual filter of main.cpp:133-140; 0 = first->second direction only             */
+    uint32_t emit_all;    /* 1 = also write matches of pairs that are not connected (tests); default 0           */
+} eacham_match_opts;
+
+#define EACHAM_PAIR_GATED 1u      /* a direction had fewer than min_dir ratio-passing matches (main.cpp:111-114) */
+#define EACHAM_PAIR_CONNECTED 2u  /* mutual count > min_mutual: the reference calls Graph::Connect (main.cpp:142-146) */
+
+typedef struct eacham_pair_result_t {
+    uint32_t n12;       /* |matches12| after the ratio test, first -> second                                  */
+    uint32_t n21;       /* |matches21| after the ratio test, second -> first                                  */
+    uint32_t n_mutual;  /* |bestMatches12| (0 when gated)                                                     */
+    uint32_t flags;     /* EACHAM_PAIR_*                                                                      */
+    uint64_t offset;    /* index of this pair's first eacham_match_t in the output buffer                     */
+    uint64_t count;     /* number of entries written for this pair (n_mutual if connected or emit_all, else 0) */
+} eacham_pair_result_t;
+
+/* Phase timings of the most recent match_pairs / commit on this handle, from CUDA events on the library's stream. */
+typedef struct eacham_gpu_timing {
+    float upload_ms;    /* descriptor H2D inside the last eacham_gpu_commit                                   */
+    float pairs_h2d_ms; /* pair list H2D                                                                      */
+    float kernel_ms;    /* matching kernels only (inputs resident in HBM)                                     */
+    float d2h_ms;       /* results + compacted matches D2H                                                    */
+    uint32_t kernel_launches; /* kernels launched by the last match_pairs                                     */
+    uint32_t reserved;
+} eacham_gpu_timing;
+
+EACHAM_API int eacham_gpu_abi_version(void);
+EACHAM_API int eacham_gpu_device_count(void);
+EACHAM_API const char* eacham_gpu_last_error(void);
+EACHAM_API void eacham_gpu_default_opts(eacham_match_opts* opts);   /* ratio 0.8, min_dir 30, min_mutual 30, cross_check 1 */
+
+EACHAM_API int eacham_gpu_create(const eacham_gpu_config* cfg, eacham_gpu_handle** out);
+EACHAM_API void eacham_gpu_destroy(eacham_gpu_handle* h);
+
+/* Stage one image's descriptors (copied; the host pointer is not retained). rows may be 0.
+ * row_stride_bytes >= 32 (ORB256) or >= 512 (F32X128): cv::Mat::step of a possibly non-continuous Mat. */
+EACHAM_API int eacham_gpu_set_descriptors(eacham_gpu_handle* h, uint32_t image_id, int kind, const void* data, uint32_t rows,
+                               size_t row_stride_bytes);
+/* Declare an image's shape without data (ranks that receive the arena by broadcast). */
+EACHAM_API int eacham_gpu_reserve(eacham_gpu_handle* h, uint32_t image_id, int kind, uint32_t rows);
+/* Lay the staged images out in the device arena and upload whatever data was staged (one H2D copy). */
+EACHAM_API int eacham_gpu_commit(eacham_gpu_handle* h);
+/* Drop all images (keeps device allocations for reuse). */
+EACHAM_API int eacham_gpu_clear(eacham_gpu_handle* h);
+
+/* Device arena after commit: the plumbing layer (torch.distributed / NCCL) broadcasts these bytes between ranks. */
+EACHAM_API int eacham_gpu_arena(eacham_gpu_handle* h, void** device_ptr, size_t* bytes);
+EACHAM_API int eacham_gpu_image_info(eacham_gpu_handle* h, uint32_t image_id, int* kind, uint32_t* rows, size_t* arena_offset);
+
+/* One direction, one pair: the reference's Match(). Synchronous, thread-safe. out gets <= cap entries, *n_out the
+ * number of ratio-passing matches (sorted by query index); EACHAM_ERR_BUFFER_TOO_SMALL if *n_out > cap. */
+EACHAM_API int eacham_gpu_match(eacham_gpu_handle* h, int kind, const void* query, uint32_t q_rows, size_t q_stride_bytes,
+                     const void* train, uint32_t t_rows, size_t t_stride_bytes, double ratio, eacham_match_t* out,
+                     size_t cap, size_t* n_out);
+
+/* kNN(k=2) only (what cv::DescriptorMatcher::knnMatch returns, FeatureMatcherFlann.cpp:17): idx[q_rows][2]
+ * (-1 = absent) and dist[q_rows][2] (float, as DMatch.distance; +inf = absent). */
+EACHAM_API int eacham_gpu_knn2(eacham_gpu_handle* h, int kind, const void* query, uint32_t q_rows, size_t q_stride_bytes,
+                    const void* train, uint32_t t_rows, size_t t_stride_bytes, int32_t* idx, float* dist);
+
+/* The batched path: for every unordered pair both directions + ratio + gates + mutual filter on the GPU
+ * (apps/sfm/main.cpp:84-147). res has n_pairs entries; matches of pair p are buf[res[p].offset .. +count),
+ * sorted by query index, query = row in image `first`, train = row in image `second`.
+ * *buf_used = entries needed; EACHAM_ERR_BUFFER_TOO_SMALL (res still valid, buf partially filled) if > buf_cap. */
+EACHAM_API int eacham_gpu_match_pairs(eacham_gpu_handle* h, const eacham_pair_t* pairs, size_t n_pairs,
+                           const eacham_match_opts* opts, eacham_pair_result_t* res, eacham_match_t* buf,
+                           size_t buf_cap, size_t* buf_used);
+
+/* Same computation with inputs AND outputs resident in HBM: enqueue, wait, no D2H of matches.
+ * Used by bench.py for the device-resident throughput figure; results stay readable via _fetch. */
+EACHAM_API int eacham_gpu_match_pairs_device(eacham_gpu_handle* h, const eacham_pair_t* pairs, size_t n_pairs,
+                                  const eacham_match_opts* opts, size_t* total_matches);
+EACHAM_API int eacham_gpu_fetch_results(eacham_gpu_handle* h, eacham_pair_result_t* res, size_t n_pairs, eacham_match_t* buf,
+                             size_t buf_cap, size_t* buf_used);
+
+EACHAM_API int eacham_gpu_last_timing(eacham_gpu_handle* h, eacham_gpu_timing* t);
+/* Write `bytes` of device memory (L2 flush between timed benchmark iterations). */
+EACHAM_API int eacham_gpu_flush_l2(eacham_gpu_handle* h, size_t bytes);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* EACHAM_GPU_H */

@@ -1,0 +1,178 @@
+"""GPU parity for the ORB (256-bit Hamming) path, through the C ABI, against the golden vectors and the oracle.
+Bit-exact: index sets, distances, counts, flags."""
+import threading
+
+import numpy as np
+import pytest
+
+from oracle import oracle as O
+import cases
+
+pytestmark = pytest.mark.gpu
+NONE = 0xFFFFFFFF
+
+
+def _map_arr(m, n):
+    a = np.full(n, NONE, np.uint32)
+    for k, v in m.items():
+        a[k] = v
+    return a
+
+
+def _assert_pair_equal(pm, want, name=""):
+    assert (pm.n12, pm.n21, pm.n_mutual, pm.gated, pm.connected) == \
+        (want["n12"], want["n21"], want["n_mutual"], bool(want["gated"]), bool(want["connected"])), name
+    assert np.array_equal(pm.matches.reshape(-1, 2), np.asarray(want["matches"]).reshape(-1, 2)), name
+
+
+def test_knn2_and_match_golden(matcher, orb_golden):
+    for name, g in orb_golden.items():
+        for q, t, idx, dist, m in ((g["d1"], g["d2"], g["idx12"], g["dist12"], g["m12"]),
+                                   (g["d2"], g["d1"], g["idx21"], g["dist21"], g["m21"])):
+            i, s = matcher.knnMatch(q, t)
+            assert np.array_equal(i, idx), name
+            assert np.array_equal(s, dist), name
+            assert np.array_equal(_map_arr(matcher.Match(q, t), q.shape[0]), m), name
+
+
+def test_match_pairs_golden_fused(matcher, orb_golden, orb_set_golden):
+    """All golden cases in ONE batched call (ragged sizes, empty images, gates at 29/30/31, ties, NaN)."""
+    names, descs, pairs = [], [], []
+    for name, g in list(orb_golden.items()) + list(orb_set_golden.items()):
+        names.append(name)
+        pairs.append((len(descs), len(descs) + 1))
+        descs += [g["d1"], g["d2"]]
+    matcher.Upload(descs)
+    allg = dict(orb_golden); allg.update(orb_set_golden)
+    for emit_all in (True, False):
+        out = matcher.MatchPairs(pairs, emit_all=emit_all)
+        for name, pm in zip(names, out):
+            n12, n21, nm, gated, conn = allg[name]["pair"].tolist()
+            want = dict(n12=n12, n21=n21, n_mutual=nm, gated=gated, connected=conn,
+                        matches=allg[name]["matches"] if (emit_all or conn) else np.zeros((0, 2), np.uint32))
+            _assert_pair_equal(pm, want, name)
+
+
+@pytest.mark.parametrize("n1,n2", [(4096, 4096), (4097, 511), (513, 4095), (1, 700), (700, 1), (2, 2), (5000, 4500), (9000, 300)])
+def test_match_pairs_vs_c_oracle_sizes(matcher, n1, n2):
+    """Row-block boundaries (512-row slots, 4096-row blocks), chunk boundaries (256 columns), tiny images."""
+    rng = np.random.default_rng(n1 * 7919 + n2)
+    a, b = cases.planted_pair(rng, n1, n2, min(n1, n2, 90) if min(n1, n2) > 40 else 0, dup_filler=False)
+    # sprinkle duplicates and zero rows to force ties in both directions
+    if n1 > 10 and n2 > 10:
+        a[3] = a[7]; b[5] = b[9]; a[1] = 0; b[2] = 0; b[4] = 0
+    matcher.Upload([a, b])
+    pm = matcher.MatchPairs([(0, 1)], emit_all=True)[0]
+    _assert_pair_equal(pm, O.c_match_pair(a, b), f"{n1}x{n2}")
+    # the transposed pair must give the transposed answer
+    pt = matcher.MatchPairs([(1, 0)], emit_all=True)[0]
+    assert (pt.n12, pt.n21, pt.n_mutual) == (pm.n21, pm.n12, pm.n_mutual)
+    assert sorted(map(tuple, pt.matches[:, ::-1].tolist())) == sorted(map(tuple, pm.matches.tolist()))
+    # one-direction API agrees with the oracle too
+    assert matcher.Match(a, b) == O.c_match(a, b)
+    i, s = matcher.knnMatch(b, a)
+    io, so = O.c_knn2(b, a)
+    assert np.array_equal(i, io) and np.array_equal(s, so)
+
+
+def test_exhaustive_set_vs_cv2(matcher):
+    """A small exhaustive image set (BASELINE config-1 shape, scaled down): every pair equals OpenCV + reference logic."""
+    from eacham_b200 import synth
+    imgs = synth.orb_image_set(12, 2048, seed=1, pool=6000)
+    pairs = synth.exhaustive_pairs(len(imgs))
+    matcher.Upload(imgs)
+    out = matcher.MatchPairs(pairs, emit_all=True)
+    ref = O.cv2_match_pair_fast if O.have_cv2() else O.c_match_pair
+    n_conn = 0
+    for (i, j), pm in zip(pairs.tolist(), out):
+        _assert_pair_equal(pm, ref(imgs[i], imgs[j]), f"pair {i},{j}")
+        n_conn += pm.connected
+    assert n_conn > 0
+
+
+def test_options_ratio_and_gates(matcher):
+    rng = np.random.default_rng(5)
+    a, b = cases.planted_pair(rng, 600, 640, 50, d_good=60)
+    import eacham_b200
+    for ratio, min_dir, min_mutual in ((0.8, 30, 30), (0.7, 10, 5), (0.95, 0, 0), (0.5, 1, 0)):
+        with eacham_b200.FeatureMatcherGpu(0.8, ratio=ratio, min_dir=min_dir, min_mutual=min_mutual) as m:
+            m.Upload([a, b])
+            pm = m.MatchPairs([(0, 1)], emit_all=True)[0]
+            _assert_pair_equal(pm, O.c_match_pair(a, b, ratio, min_dir, min_mutual), f"ratio {ratio}")
+            assert m.Match(a, b) == O.c_match(a, b, ratio)
+    with eacham_b200.FeatureMatcherGpu(0.8, cross_check=False) as m:      # first -> second direction only
+        m.Upload([a, b])
+        pm = m.MatchPairs([(0, 1)], emit_all=True)[0]
+        assert pm.best12() == O.c_match(a, b)
+
+
+def test_strided_rows(matcher):
+    """cv::Mat with step > cols (a ROI): the ABI takes (ptr, rows, step)."""
+    rng = np.random.default_rng(11)
+    big = rng.integers(0, 256, (300, 48), dtype=np.uint8)
+    q = big[:, :32]; t = big[::-1][:150, 8:40]
+    assert not q.flags["C_CONTIGUOUS"]
+    assert matcher.Match(q, t) == O.c_match(np.ascontiguousarray(q), np.ascontiguousarray(t))
+    matcher.Upload([q, t])
+    pm = matcher.MatchPairs([(0, 1)], emit_all=True)[0]
+    _assert_pair_equal(pm, O.c_match_pair(np.ascontiguousarray(q), np.ascontiguousarray(t)))
+
+
+def test_concurrent_match_calls_on_one_handle(matcher):
+    """The reference calls Match concurrently on ONE matcher from TBB workers (main.cpp:98-109)."""
+    rng = np.random.default_rng(3)
+    sets = [cases.planted_pair(rng, 300 + 17 * k, 280 + 13 * k, 40) for k in range(8)]
+    want = [O.c_match(a, b) for a, b in sets]
+    got = [None] * len(sets)
+
+    def work(k):
+        for _ in range(3):
+            got[k] = matcher.Match(*sets[k])
+
+    th = [threading.Thread(target=work, args=(k,)) for k in range(len(sets))]
+    [t.start() for t in th]; [t.join() for t in th]
+    assert got == want
+
+
+def test_error_codes(matcher):
+    from eacham_b200 import _lib as L
+    import eacham_b200
+    with eacham_b200.FeatureMatcherGpu(0.8) as m:
+        with pytest.raises(L.EachamGpuError) as e:
+            m.MatchPairs([(0, 1)])
+        assert e.value.code == L.ERR_NOT_COMMITTED
+        m.Upload([np.zeros((4, 32), np.uint8), np.zeros((4, 128), np.float32)])
+        with pytest.raises(L.EachamGpuError) as e:
+            m.MatchPairs([(0, 1)])
+        assert e.value.code == L.ERR_KIND_MISMATCH
+        with pytest.raises(L.EachamGpuError) as e:
+            m.MatchPairs([(0, 7)])
+        assert e.value.code == L.ERR_NOT_COMMITTED
+        with pytest.raises(TypeError):
+            m.Match(np.zeros((4, 31), np.uint8), np.zeros((4, 32), np.uint8))
+
+
+def test_buffer_too_small_reports_need(matcher):
+    rng = np.random.default_rng(8)
+    a, b = cases.planted_pair(rng, 300, 300, 60)
+    matcher.Upload([a, b])
+    tiny = np.empty(10, dtype=[("query", "<u4"), ("train", "<u4")])
+    res, buf = matcher.MatchPairsRaw([(0, 1)], buf=tiny)      # wrapper retries through fetch_results
+    assert res["n_mutual"][0] == 60 and buf.shape[0] == 60
+
+
+def test_full_size_properties(matcher):
+    """BASELINE config-2 shape (4k ORB per image), size-independent properties instead of a CPU oracle:
+    an image against a row-permuted copy of itself must return exactly the permutation for every unique row."""
+    from eacham_b200 import synth
+    img = synth.orb_image_set(1, 4096, seed=2, pool=20000, dup_frac=0.0, zero_rows=0)[0]
+    rng = np.random.default_rng(2)
+    perm = rng.permutation(4096)
+    matcher.Upload([img, np.ascontiguousarray(img[perm])])
+    pm = matcher.MatchPairs([(0, 1)], emit_all=True)[0]
+    inv = np.empty(4096, np.int64); inv[perm] = np.arange(4096)
+    assert pm.n12 == 4096 and pm.n21 == 4096 and pm.n_mutual == 4096 and pm.connected
+    assert np.array_equal(pm.matches[:, 0], np.arange(4096)) and np.array_equal(pm.matches[:, 1], inv)
+    # idempotence / determinism: same call, same bytes
+    pm2 = matcher.MatchPairs([(0, 1)], emit_all=True)[0]
+    assert np.array_equal(pm.matches, pm2.matches)

@@ -1,0 +1,151 @@
+// Pipe-throughput microbenchmark for the ORB Hamming kernel design (sm_100a).
+// Measures lane-ops / clk / SM for the instructions the XOR+POPC+top-2 inner loop is made of,
+// so that the POPC-bound roofline in DESIGN.md rests on a measured figure, not the table value.
+// Build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o pipe_microbench pipe_microbench.cu
+#include <cstdio>
+#include <cstdint>
+#include <cuda_runtime.h>
+
+#define CK(x) do { cudaError_t e = (x); if (e != cudaSuccess) { printf("CUDA error %s at %d\n", cudaGetErrorString(e), __LINE__); return 1; } } while (0)
+
+constexpr int ITERS = 4096;
+constexpr int CHAINS = 8;
+
+enum Op { POPC, LOP3, IADD3, IMAD, VIMNMX, VIADDMNMX, REDUX, SHFL, MIX_DIST, MIX_DIST_TOP2 };
+
+template <int OP>
+__global__ void __launch_bounds__(1024, 1) bench(uint32_t* out, long long* cycles, uint32_t seed) {
+    uint32_t a[CHAINS];
+#pragma unroll
+    for (int i = 0; i < CHAINS; ++i) a[i] = seed * (threadIdx.x + 1) + i * 0x9e3779b9u;
+    uint32_t k = seed | 1u, k2 = seed * 3u;
+    __syncthreads();
+    long long t0 = clock64();
+#pragma unroll 1
+    for (int it = 0; it < ITERS; ++it) {
+#pragma unroll
+        for (int i = 0; i < CHAINS; ++i) {
+            if (OP == POPC) asm volatile("popc.b32 %0, %0;" : "+r"(a[i]));
+            else if (OP == LOP3) asm volatile("xor.b32 %0, %0, %1;" : "+r"(a[i]) : "r"(k));
+            else if (OP == IADD3) asm volatile("add.u32 %0, %0, %1;" : "+r"(a[i]) : "r"(k));
+            else if (OP == IMAD) asm volatile("mad.lo.u32 %0, %0, %1, %2;" : "+r"(a[i]) : "r"(k), "r"(k2));
+            else if (OP == VIMNMX) asm volatile("min.u32 %0, %0, %1;" : "+r"(a[i]) : "r"(k + i + it));
+            else if (OP == VIADDMNMX) a[i] = __viaddmin_u32(a[i], k, k2 + it);
+            else if (OP == REDUX) asm volatile("redux.sync.min.u32 %0, %0, 0xffffffff;" : "+r"(a[i]));
+            else if (OP == SHFL) asm volatile("shfl.sync.bfly.b32 %0, %0, 1, 0x1f, 0xffffffff;" : "+r"(a[i]));
+        }
+    }
+    long long t1 = clock64();
+    uint32_t s = 0;
+#pragma unroll
+    for (int i = 0; i < CHAINS; ++i) s += a[i];
+    out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+    if (threadIdx.x == 0) cycles[blockIdx.x] = t1 - t0;
+}
+
+// The real mix: 8 rows held in registers against a stream of columns (from smem, broadcast).
+// TOP2 = 0: distance only (8 LOP3 + 8 POPC + 4 IADD3 per distance), accumulate min.
+// TOP2 = 1: + packed-key top-2 in both directions (the planned inner loop).
+template <int TOP2>
+__global__ void __launch_bounds__(512, 1) mix(uint32_t* out, long long* cycles, uint32_t seed, int ncols) {
+    __shared__ uint4 cols[2 * 256];
+    for (int i = threadIdx.x; i < 512; i += blockDim.x) {
+        uint32_t v = seed * (i + 7);
+        cols[i] = make_uint4(v, v * 3, v * 5, v * 7);
+    }
+    uint32_t a[8][8];
+#pragma unroll
+    for (int r = 0; r < 8; ++r)
+#pragma unroll
+        for (int w = 0; w < 8; ++w) a[r][w] = seed * (threadIdx.x * 64 + r * 8 + w + 1);
+    uint32_t m0[8], m1[8];
+#pragma unroll
+    for (int r = 0; r < 8; ++r) { m0[r] = 0xffffffffu; m1[r] = 0xffffffffu; }
+    uint32_t acc = 0;
+    __syncthreads();
+    long long t0 = clock64();
+#pragma unroll 1
+    for (int j = 0; j < ncols; ++j) {
+        uint4 b0 = cols[(j & 255) * 2], b1 = cols[(j & 255) * 2 + 1];
+        uint32_t c0 = 0xffffffffu, c1 = 0xffffffffu;
+#pragma unroll
+        for (int r = 0; r < 8; ++r) {
+            uint32_t d = __popc(a[r][0] ^ b0.x) + __popc(a[r][1] ^ b0.y) + __popc(a[r][2] ^ b0.z) + __popc(a[r][3] ^ b0.w)
+                       + __popc(a[r][4] ^ b1.x) + __popc(a[r][5] ^ b1.y) + __popc(a[r][6] ^ b1.z) + __popc(a[r][7] ^ b1.w);
+            if (TOP2) {
+                uint32_t kr = (d << 16) + j;
+                uint32_t kc = (d << 16) + r;
+                m1[r] = min(m1[r], max(m0[r], kr)); m0[r] = min(m0[r], kr);
+                c1 = min(c1, max(c0, kc)); c0 = min(c0, kc);
+            } else {
+                m0[r] = min(m0[r], d);
+            }
+        }
+        if (TOP2) {
+            uint32_t g0 = __reduce_min_sync(0xffffffffu, c0);
+            uint32_t x = (c0 == g0) ? c1 : c0;
+            uint32_t g1 = __reduce_min_sync(0xffffffffu, x);
+            acc += g0 ^ g1;
+        }
+    }
+    long long t1 = clock64();
+    uint32_t s = acc;
+#pragma unroll
+    for (int r = 0; r < 8; ++r) s += m0[r] ^ m1[r];
+    out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+    if (threadIdx.x == 0) cycles[blockIdx.x] = t1 - t0;
+}
+
+template <int OP>
+int run(const char* name, int threads, uint32_t* out, long long* cyc, int nsm) {
+    bench<OP><<<nsm, threads>>>(out, cyc, 12345u);
+    CK(cudaDeviceSynchronize());
+    cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
+    cudaEventRecord(e0);
+    bench<OP><<<nsm, threads>>>(out, cyc, 12345u);
+    cudaEventRecord(e1);
+    CK(cudaDeviceSynchronize());
+    float ms; cudaEventElapsedTime(&ms, e0, e1);
+    long long h[256]; CK(cudaMemcpy(h, cyc, sizeof(long long) * nsm, cudaMemcpyDeviceToHost));
+    long long mx = 0; for (int i = 0; i < nsm; ++i) mx = h[i] > mx ? h[i] : mx;
+    double ops = (double)threads * ITERS * CHAINS;
+    printf("{\"op\": \"%s\", \"threads_per_sm\": %d, \"lane_ops_per_clk_per_sm\": %.2f, \"cycles\": %lld, \"ms\": %.4f, \"implied_mhz\": %.0f}\n",
+           name, threads, ops / (double)mx, mx, ms, (double)mx / (ms * 1e3));
+    return 0;
+}
+
+int main() {
+    cudaDeviceProp p; CK(cudaGetDeviceProperties(&p, 0));
+    int nsm = p.multiProcessorCount;
+    printf("{\"device\": \"%s\", \"sms\": %d, \"cc\": \"%d.%d\", \"clock_khz\": %d}\n", p.name, nsm, p.major, p.minor, p.clockRate);
+    uint32_t* out; long long* cyc;
+    CK(cudaMalloc(&out, sizeof(uint32_t) * nsm * 1024));
+    CK(cudaMalloc(&cyc, sizeof(long long) * 256));
+    for (int threads : {256, 512, 1024}) {
+        run<POPC>("popc", threads, out, cyc, nsm);
+        run<LOP3>("lop3_xor", threads, out, cyc, nsm);
+        run<IADD3>("iadd", threads, out, cyc, nsm);
+        run<IMAD>("imad", threads, out, cyc, nsm);
+        run<VIMNMX>("vimnmx_min", threads, out, cyc, nsm);
+        run<VIADDMNMX>("viaddmin", threads, out, cyc, nsm);
+        run<REDUX>("redux_min", threads, out, cyc, nsm);
+        run<SHFL>("shfl_bfly", threads, out, cyc, nsm);
+    }
+    for (int top2 = 0; top2 < 2; ++top2) {
+        int ncols = 4096;
+        for (int rep = 0; rep < 2; ++rep) {
+            cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
+            cudaEventRecord(e0);
+            if (top2) mix<1><<<nsm, 512>>>(out, cyc, 977u, ncols); else mix<0><<<nsm, 512>>>(out, cyc, 977u, ncols);
+            cudaEventRecord(e1);
+            CK(cudaDeviceSynchronize());
+            float ms; cudaEventElapsedTime(&ms, e0, e1);
+            long long h[256]; CK(cudaMemcpy(h, cyc, sizeof(long long) * nsm, cudaMemcpyDeviceToHost));
+            long long mx = 0; for (int i = 0; i < nsm; ++i) mx = h[i] > mx ? h[i] : mx;
+            double dists = 512.0 * 8 * ncols;
+            if (rep) printf("{\"op\": \"mix_dist%s\", \"distances_per_clk_per_sm\": %.3f, \"popc_per_clk_per_sm\": %.2f, \"cycles\": %lld, \"ms\": %.4f, \"implied_mhz\": %.0f}\n",
+                   top2 ? "_top2_both_dirs" : "_only", dists / mx, 8 * dists / mx, mx, ms, (double)mx / (ms * 1e3));
+        }
+    }
+    return 0;
+}
