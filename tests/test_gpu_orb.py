@@ -176,3 +176,15 @@ def test_full_size_properties(matcher):
     # idempotence / determinism: same call, same bytes
     pm2 = matcher.MatchPairs([(0, 1)], emit_all=True)[0]
     assert np.array_equal(pm.matches, pm2.matches)
+
+
+def test_cpp_shim_program():
+    """include/eacham/FeatureMatcherGpu.h driven like apps/sfm/main.cpp drives its matcher (threads + batched)."""
+    import os, subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = os.path.join(root, "tests", "cpp", "shim_test.bin")
+    subprocess.run(["g++", "-std=c++17", "-O2", "-I" + os.path.join(root, "include"), os.path.join(root, "tests", "cpp", "shim_test.cpp"),
+                    "-L" + os.path.join(root, "eacham_b200"), "-leacham_gpu", "-lpthread", "-o", exe], check=True)
+    env = dict(os.environ, LD_LIBRARY_PATH=os.path.join(root, "eacham_b200") + ":" + os.environ.get("LD_LIBRARY_PATH", ""))
+    r = subprocess.run([exe], env=env, capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout + r.stderr
