@@ -19,6 +19,7 @@
 #include "../../include/eacham_gpu.h"
 #include "l2_kernels.cuh"
 #include "orb_kernels.cuh"
+#include "sift_tc_kernels.cuh"
 
 namespace {
 
@@ -90,6 +91,14 @@ struct eacham_gpu_handle {
     size_t arena_bytes = 0;
     DevBuf<eacham::orb::ImageDesc> d_images;
     uint32_t max_rows[2] = {0, 0};
+    // SIFT tensor-core path: pre-tiled bf16 copy of every F32X128 image, built lazily after commit (+ broadcast)
+    DevBuf<uint8_t> tc_arena;
+    DevBuf<eacham::sift::ImageDescTc> d_images_tc;
+    std::vector<size_t> tc_offsets;
+    size_t tc_bytes = 0;
+    bool tc_dirty = true;
+    DevBuf<uint8_t> tc_scratch;
+    uint32_t cfg_flags = 0;
 
     DevBuf<eacham_pair_t> d_pairs;
     DevBuf<eacham_pair_result_t> d_results;
@@ -186,6 +195,7 @@ int eacham_gpu_create(const eacham_gpu_config* cfg, eacham_gpu_handle** out) {
     h->sm_count = prop.multiProcessorCount;
     h->smem_optin = prop.sharedMemPerBlockOptin;
     h->cfg_match_entries = cfg ? cfg->match_buffer_entries : 0;
+    h->cfg_flags = cfg ? cfg->flags : 0;
     DeviceGuard g(dev);
     cudaError_t e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking);
     for (int i = 0; i < 8 && e == cudaSuccess; ++i) e = cudaEventCreate(&h->ev[i]);
@@ -200,6 +210,7 @@ void eacham_gpu_destroy(eacham_gpu_handle* h) {
     {
         DeviceGuard g(h->device);
         cudaStreamSynchronize(h->stream);
+        h->tc_arena.release(); h->d_images_tc.release(); h->tc_scratch.release();
         h->arena.release(); h->d_images.release(); h->d_pairs.release(); h->d_results.release(); h->d_matches.release();
         h->d_counter.release(); h->d_cursor.release(); h->d_q.release(); h->d_t.release(); h->d_partial.release();
         h->d_idx.release(); h->d_dist.release(); h->d_match.release(); h->d_match2.release(); h->d_flush.release();
@@ -264,6 +275,16 @@ int eacham_gpu_commit(eacham_gpu_handle* h) {
         table[i].kind = im.present ? (uint32_t)im.kind : 0xffffffffu;
         if (im.present) h->max_rows[im.kind] = std::max(h->max_rows[im.kind], im.rows);
     }
+    h->tc_offsets.assign(h->images.size(), 0);
+    h->tc_bytes = 0;
+    for (size_t i = 0; i < h->images.size(); ++i) {
+        const ImageHost& im = h->images[i];
+        if (im.present && im.kind == EACHAM_KIND_F32X128) {
+            h->tc_offsets[i] = h->tc_bytes;
+            h->tc_bytes += (size_t)((im.rows + 127) / 128) * eacham::tc::kBlockBytes;
+        }
+    }
+    h->tc_dirty = true;
     CUDA_TRY(cudaEventRecord(h->ev[0], h->stream));
     if (h->any_data && h->staging_used > 0)
         CUDA_TRY(cudaMemcpyAsync(h->arena.p, h->staging, h->staging_used, cudaMemcpyHostToDevice, h->stream));
@@ -431,6 +452,33 @@ int eacham_gpu_match(eacham_gpu_handle* h, int kind, const void* query, uint32_t
 // -------------------------------------------------------------------------------------------------------------
 namespace {
 
+// Builds the pre-tiled bf16 copy (tc_common.cuh layout) of every F32X128 image from the fp32 arena. Runs lazily at the
+// first SIFT match_pairs after a commit, i.e. after a possible NCCL broadcast has filled the arena on this rank.
+int prepare_tc(eacham_gpu_handle* h) {
+    using namespace eacham;
+    if (!h->tc_dirty) return EACHAM_OK;
+    int rc;
+    if ((rc = h->tc_arena.ensure(std::max(h->tc_bytes, (size_t)tc::kBlockBytes)))) return rc;
+    if ((rc = h->d_images_tc.ensure(std::max(h->images.size(), (size_t)1)))) return rc;
+    std::vector<sift::ImageDescTc> table(h->images.size());
+    for (size_t i = 0; i < h->images.size(); ++i) {
+        const ImageHost& im = h->images[i];
+        table[i].offset = im.offset; table[i].tc_offset = h->tc_offsets[i];
+        table[i].rows = im.present ? im.rows : 0; table[i].kind = im.present ? (uint32_t)im.kind : 0xffffffffu;
+        if (im.present && im.kind == EACHAM_KIND_F32X128 && im.rows > 0) {
+            const uint32_t nblk = (im.rows + 127) / 128;
+            sift::sift_prep_kernel<<<nblk * 16, 256, 0, h->stream>>>(reinterpret_cast<const float*>(h->arena.p + im.offset), im.rows,
+                                                                      h->tc_arena.p + h->tc_offsets[i], nblk);
+        }
+    }
+    CUDA_TRY(cudaGetLastError());
+    if (!table.empty())
+        CUDA_TRY(cudaMemcpyAsync(h->d_images_tc.p, table.data(), table.size() * sizeof(table[0]), cudaMemcpyHostToDevice, h->stream));
+    CUDA_TRY(cudaStreamSynchronize(h->stream));
+    h->tc_dirty = false;
+    return EACHAM_OK;
+}
+
 int launch_pairs(eacham_gpu_handle* h, const eacham_pair_t* pairs, size_t n_pairs, const eacham_match_opts* opts_in) {
     using namespace eacham;
     if (!h->committed) return fail(EACHAM_ERR_NOT_COMMITTED, "eacham_gpu_match_pairs called before eacham_gpu_commit");
@@ -464,6 +512,7 @@ int launch_pairs(eacham_gpu_handle* h, const eacham_pair_t* pairs, size_t n_pair
                                                : std::max((size_t)1 << 20, n_pairs * (size_t)192);
     if (h->d_matches.cap < want_entries && (rc = h->d_matches.ensure(want_entries))) return rc;
 
+    if (kind == EACHAM_KIND_F32X128 && !(h->cfg_flags & 1u) && (rc = prepare_tc(h))) return rc;
     CUDA_TRY(cudaEventRecord(h->ev[2], h->stream));
     CUDA_TRY(cudaMemcpyAsync(h->d_pairs.p, pairs, n_pairs * sizeof(eacham_pair_t), cudaMemcpyHostToDevice, h->stream));
     CUDA_TRY(cudaEventRecord(h->ev[3], h->stream));
@@ -487,8 +536,23 @@ int launch_pairs(eacham_gpu_handle* h, const eacham_pair_t* pairs, size_t n_pair
             orb::orb_match_pairs_kernel<<<grid, orb::kThreads, smem, h->stream>>>(p);
             CUDA_TRY(cudaGetLastError());
             h->timing.kernel_launches += 1;
+        } else if (kind == EACHAM_KIND_F32X128 && !(h->cfg_flags & 1u)) {
+            // tensor-core scorer + exact FP32 re-rank, one persistent CTA per pair
+            sift::PairParamsTc p;
+            p.arena = h->arena.p; p.tc_arena = h->tc_arena.p; p.images = h->d_images_tc.p; p.pairs = h->d_pairs.p; p.n_pairs = (uint32_t)n_pairs;
+            p.ratio = o.ratio; p.min_dir = o.min_dir; p.min_mutual = o.min_mutual; p.cross_check = o.cross_check; p.emit_all = o.emit_all;
+            p.results = h->d_results.p; p.matches = h->d_matches.p; p.matches_cap = h->d_matches.cap; p.cursor = h->d_cursor.p;
+            p.rows_cap = (uint32_t)align_up(std::max(max_first, 1u), 128); p.cols_cap = (uint32_t)align_up(std::max(max_second, 1u), 128);
+            const unsigned grid = (unsigned)std::min<size_t>(n_pairs, (size_t)h->sm_count);
+            if ((rc = h->tc_scratch.ensure(sift::tc_scratch_bytes_per_cta(p.rows_cap, p.cols_cap) * grid))) return rc;
+            p.scratch = h->tc_scratch.p;
+            const size_t smem = sizeof(sift::SmemTc) + 128;
+            CUDA_TRY(cudaFuncSetAttribute(sift::sift_match_pairs_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            sift::sift_match_pairs_kernel<<<grid, sift::kThreadsTc, smem, h->stream>>>(p);
+            CUDA_TRY(cudaGetLastError());
+            h->timing.kernel_launches += 1;
         } else {
-            // exact per-pair path: two kNN directions + finalisation (SIFT FP32; ORB images beyond the fused limit)
+            // exact per-pair path: two kNN directions + finalisation (SIFT all-FP32 when cfg.flags & 1; ORB beyond the fused limit)
             const uint32_t max_rows = std::max(max_first, max_second);
             if ((rc = h->d_match.ensure(max_rows)) || (rc = h->d_match2.ensure(max_rows))) return rc;
             for (size_t i = 0; i < n_pairs; ++i) {

@@ -1,0 +1,458 @@
+// sift_tc_kernels.cuh -- 128-d float (SIFT) matching on the 5th-gen tensor cores (tcgen05) of sm_100a.
+//
+// Replaces, for N x 128 CV_32F descriptors, per unordered image pair:
+//   knnMatch(k=2) both directions   /root/reference/modules/base/features/FeatureMatcherFlann.cpp:17  (exact NORM_L2 semantics)
+//   ratio test                      /root/reference/modules/base/features/FeatureMatcherFlann.cpp:21-27
+//   gates + mutual filter           /root/reference/apps/sfm/main.cpp:111-146
+// Candidate scoring runs as a bf16 GEMM with fp32 accumulation in tensor memory; the two best candidates per row and
+// per column are then re-ranked with exact FP32 arithmetic (sqrtf(sum (a-b)^2), float accumulator) so that the
+// distances the ratio test sees are the reference's. See DESIGN.md "SIFT kernel".
+#pragma once
+#include <cstdint>
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include "../../include/eacham_gpu.h"
+#include "tc_common.cuh"
+
+namespace eacham {
+namespace sift {
+
+// x = hi + mid + lo exactly (24-bit significand -> 3 x 8 bits)
+__device__ __forceinline__ void split3(float x, __nv_bfloat16& hi, __nv_bfloat16& mid, __nv_bfloat16& lo) {
+    hi = __float2bfloat16_rn(x);
+    const float r1 = x - __bfloat162float(hi);
+    mid = __float2bfloat16_rn(r1);
+    const float r2 = r1 - __bfloat162float(mid);
+    lo = __float2bfloat16_rn(r2);
+}
+
+// fp32 rows [rows][128] -> pre-tiled bf16 blocks (tc_common.cuh layout). One warp per row; grid covers
+// n_blocks * 128 rows (rows >= `rows` are padding: zero data, norm 1e30 so they never win a minimum).
+__global__ void __launch_bounds__(256) sift_prep_kernel(const float* __restrict__ src, uint32_t rows, uint8_t* __restrict__ dst,
+                                                        uint32_t n_blocks) {
+    const uint32_t row = blockIdx.x * 8 + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (row >= n_blocks * tc::kBlockRows) return;
+    uint8_t* blk = dst + (size_t)(row / tc::kBlockRows) * tc::kBlockBytes;
+    const uint32_t r = row % tc::kBlockRows;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (row < rows) v = __ldg(reinterpret_cast<const float4*>(src + (size_t)row * 128) + lane);
+    const __nv_bfloat16 b0 = __float2bfloat16_rn(v.x), b1 = __float2bfloat16_rn(v.y), b2 = __float2bfloat16_rn(v.z),
+                        b3 = __float2bfloat16_rn(v.w);
+    const float f0 = __bfloat162float(b0), f1 = __bfloat162float(b1), f2 = __bfloat162float(b2), f3 = __bfloat162float(b3);
+    float n = f0 * f0 + f1 * f1 + f2 * f2 + f3 * f3;       // norm of the ROUNDED row: D = |a-b|^2/2 stays consistent
+#pragma unroll
+    for (int o = 16; o >= 1; o >>= 1) n += __shfl_xor_sync(0xffffffffu, n, o);
+    // lane l holds dims 4l..4l+3 -> chunk l/2, bytes (l&1)*8 .. +8 of the row's 16-byte slot
+    __nv_bfloat162 p0 = __halves2bfloat162(b0, b1), p1 = __halves2bfloat162(b2, b3);
+    uint2 packed;
+    packed.x = *reinterpret_cast<uint32_t*>(&p0);
+    packed.y = *reinterpret_cast<uint32_t*>(&p1);
+    *reinterpret_cast<uint2*>(blk + (size_t)(lane >> 1) * tc::kChunkStride + r * 16 + (lane & 1) * 8) = packed;
+    if (lane < 4) {
+        // augmentation: 16 bf16 as A operand (chunks 16,17), 16 bf16 as B operand (chunks 18,19); lanes 0..3 write
+        // one 16-byte slot each
+        const float x = (row < rows) ? -0.5f * n : -1e30f;
+        __nv_bfloat16 hi, mid, lo;
+        split3(x, hi, mid, lo);
+        const __nv_bfloat16 one = __float2bfloat16_rn(1.f), zero = __float2bfloat16_rn(0.f);
+        __nv_bfloat16 e[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) e[k] = zero;
+        if (lane == 0) { e[0] = hi; e[1] = mid; e[2] = lo; e[3] = one; e[4] = one; e[5] = one; }       // A-role, first chunk
+        if (lane == 2) { e[0] = one; e[1] = one; e[2] = one; e[3] = hi; e[4] = mid; e[5] = lo; }       // B-role, first chunk
+        uint4 w;
+        __nv_bfloat162 q0 = __halves2bfloat162(e[0], e[1]), q1 = __halves2bfloat162(e[2], e[3]), q2 = __halves2bfloat162(e[4], e[5]),
+                       q3 = __halves2bfloat162(e[6], e[7]);
+        w.x = *reinterpret_cast<uint32_t*>(&q0); w.y = *reinterpret_cast<uint32_t*>(&q1);
+        w.z = *reinterpret_cast<uint32_t*>(&q2); w.w = *reinterpret_cast<uint32_t*>(&q3);
+        *reinterpret_cast<uint4*>(blk + (size_t)(tc::kDataChunks + lane) * tc::kChunkStride + r * 16) = w;
+    }
+}
+
+// =============================================================================================================
+// The fused SIFT pair kernel.
+//
+// One persistent CTA per image pair (static round-robin over the pair list). 320 threads:
+//   warp 0    producer: 1-D bulk copies (TMA engine) of pre-tiled bf16 blocks, mbarrier pipeline
+//   warp 1    MMA issuer: one thread issues tcgen05.mma (M=128, N=128, K=16) x 9 k-steps x 2 row halves per tile
+//   warps 2-9 epilogue: tcgen05.ld -> packed-key top-2 for rows (registers) and columns (REDUX + smem slots)
+// A block of 256 rows of the first image stays in shared memory while the second image streams through in
+// 128-column tiles (3 stages). Accumulators: 2 stages x 2 halves x 128 fp32 columns = all 512 TMEM columns, so the
+// tensor core fills stage s+1 while the epilogue drains stage s.
+// TMEM holds D = |a-b|^2/2 of the bf16-rounded rows (norms folded into the GEMM: tc_common.cuh). Keys: the low 8
+// mantissa bits of D are replaced by an index byte (column within the thread's 64 columns / row within the 256-row
+// block), so integer min/max on the bit pattern orders by (distance, index) and REDUX.MIN works on it. Coarse
+// indices (tile id, block id) are tracked per tile, not per element.
+// After a row block's sweep the two candidates of every row are re-ranked exactly in FP32 from the original
+// fp32 rows, the ratio test is applied, and at the end of the pair the same happens for columns, followed by the
+// reference's gates / mutual filter / compaction -- all inside the CTA.
+// =============================================================================================================
+struct ImageDescTc {
+    unsigned long long offset;      // fp32 rows in the arena
+    unsigned long long tc_offset;   // pre-tiled bf16 blocks in the tc arena
+    uint32_t rows;
+    uint32_t kind;
+};
+
+struct PairParamsTc {
+    const uint8_t* arena;           // fp32 descriptors (exact re-rank)
+    const uint8_t* tc_arena;        // bf16 blocks (scoring)
+    const ImageDescTc* images;
+    const eacham_pair_t* pairs;
+    uint32_t n_pairs;
+    double ratio;
+    uint32_t min_dir, min_mutual, cross_check, emit_all;
+    eacham_pair_result_t* results;
+    eacham_match_t* matches;
+    unsigned long long matches_cap;
+    unsigned long long* cursor;
+    uint8_t* scratch;               // per CTA: colstate (16 B x cols_cap) + m12 (4 B x rows_cap) + m21 (4 B x cols_cap)
+    uint32_t rows_cap, cols_cap;    // multiples of 128
+};
+
+constexpr int kEpiWarps = 8;
+constexpr int kEpiThreads = kEpiWarps * 32;
+constexpr int kThreadsTc = 64 + kEpiThreads;
+constexpr int kBStages = 3;
+constexpr int kAccStages = 2;
+constexpr int kABlockRows = 256;
+constexpr int32_t kEmptyKeyTc = 0x7F7FFF00;
+constexpr long long kEmptyComp = ((long long)0x7F7FFF << 32) | 0xFFFFFFFFll;
+
+__host__ __device__ inline size_t tc_scratch_bytes_per_cta(uint32_t rows_cap, uint32_t cols_cap) {
+    return (size_t)cols_cap * 16 + (size_t)rows_cap * 4 + (size_t)cols_cap * 4;
+}
+
+struct SmemTc {
+    uint8_t a[2][tc::kAOperandBytes];
+    uint8_t b[kBStages][tc::kAOperandBytes];
+    uint2 slots[2][4][128];
+    int4 rowkeys[kABlockRows];          // cp=1 partial row state: m0, m1, t0, t1
+    uint2 rowcand[kABlockRows];         // merged candidates j0, j1
+    uint64_t b_full[kBStages], b_empty[kBStages], a_full, a_empty, acc_full[kAccStages], acc_empty[kAccStages];
+    uint32_t tmem_slot;
+    uint32_t red[2 * kEpiWarps + 8];
+    unsigned long long base;
+};
+
+__device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory"); }
+
+__device__ __forceinline__ void comp_merge(long long b0, long long b1, long long& m0, long long& m1) {
+    const long long lo = b0 < m0 ? b0 : m0;
+    const long long mx = b0 < m0 ? m0 : b0;
+    const long long mn = b1 < m1 ? b1 : m1;
+    m0 = lo;
+    m1 = mx < mn ? mx : mn;
+}
+
+// exact reference distance: sqrtf(sum_k (a_k - b_k)^2), float accumulator; all lanes return the same value
+__device__ __forceinline__ float exact_l2(const float4 a4, const float* __restrict__ brow, int lane) {
+    const float4 b4 = __ldg(reinterpret_cast<const float4*>(brow) + lane);
+    const float dx = a4.x - b4.x, dy = a4.y - b4.y, dz = a4.z - b4.z, dw = a4.w - b4.w;
+    float s = dx * dx;
+    s = fmaf(dy, dy, s); s = fmaf(dz, dz, s); s = fmaf(dw, dw, s);
+#pragma unroll
+    for (int o = 16; o >= 1; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    return __fsqrt_rn(s);
+}
+
+// re-rank two candidates of one query row exactly, apply the ratio test; returns the train index or EACHAM_NONE
+__device__ __forceinline__ uint32_t rerank_ratio(const float* __restrict__ qrow, const float* __restrict__ tbase, uint32_t j0,
+                                                 uint32_t j1, uint32_t n_train, double ratio, int lane) {
+    const float4 a4 = __ldg(reinterpret_cast<const float4*>(qrow) + lane);
+    const bool v0 = j0 < n_train, v1 = j1 < n_train;
+    float d0 = v0 ? exact_l2(a4, tbase + (size_t)j0 * 128, lane) : __int_as_float(0x7f800000);
+    float d1 = v1 ? exact_l2(a4, tbase + (size_t)j1 * 128, lane) : __int_as_float(0x7f800000);
+    if (d1 < d0 || (d1 == d0 && j1 < j0)) { const float t = d0; d0 = d1; d1 = t; const uint32_t u = j0; j0 = j1; j1 = u; }
+    if (!(v0 && v1)) return EACHAM_NONE;                 // fewer than two neighbours: reference is UB, rejected
+    return ((double)__fdiv_rn(d0, d1) < ratio) ? j0 : EACHAM_NONE;
+}
+
+template <int NH>
+__device__ __forceinline__ void epi_tile(uint32_t acc_taddr, int cp, int q, int lane, int32_t (&m0)[2], int32_t (&m1)[2],
+                                         uint2* __restrict__ slot_q) {
+    const uint32_t ridx0 = q * 32 + lane, ridx1 = 128 + q * 32 + lane;
+#pragma unroll
+    for (int ch = 0; ch < 4; ++ch) {
+        uint32_t v0[16], v1[16];
+        tc::tmem_ld16(acc_taddr + cp * 64 + ch * 16, v0);
+        if (NH == 2) tc::tmem_ld16(acc_taddr + 128 + cp * 64 + ch * 16, v1);
+        tc::tmem_ld_wait();
+#pragma unroll
+        for (int k = 0; k < 16; ++k) {
+            const uint32_t idx = ch * 16 + k;
+            const int32_t kr0 = (int32_t)((v0[k] & 0xFFFFFF00u) | idx);
+            m1[0] = min(m1[0], max(m0[0], kr0));
+            m0[0] = min(m0[0], kr0);
+            int32_t lo = (int32_t)((v0[k] & 0xFFFFFF00u) | ridx0), hi = kEmptyKeyTc;
+            if (NH == 2) {
+                const int32_t kr1 = (int32_t)((v1[k] & 0xFFFFFF00u) | idx);
+                m1[1] = min(m1[1], max(m0[1], kr1));
+                m0[1] = min(m0[1], kr1);
+                const int32_t kc1 = (int32_t)((v1[k] & 0xFFFFFF00u) | ridx1);
+                hi = max(lo, kc1);
+                lo = min(lo, kc1);
+            }
+            const int32_t g0 = __reduce_min_sync(0xffffffffu, lo);
+            const int32_t x = (lo == g0) ? hi : lo;
+            const int32_t g1 = __reduce_min_sync(0xffffffffu, x);
+            if (lane == (int)(idx & 31)) slot_q[cp * 64 + idx] = make_uint2((uint32_t)g0, (uint32_t)g1);
+        }
+    }
+}
+
+__global__ void __launch_bounds__(kThreadsTc, 1) sift_match_pairs_kernel(const PairParamsTc p) {
+    extern __shared__ __align__(128) uint8_t smem_raw[];
+    SmemTc& S = *reinterpret_cast<SmemTc*>(smem_raw);
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+
+    if (tid == 0) {
+        for (int s = 0; s < kBStages; ++s) { tc::mbar_init(&S.b_full[s], 1); tc::mbar_init(&S.b_empty[s], 1); }
+        tc::mbar_init(&S.a_full, 1); tc::mbar_init(&S.a_empty, 1);
+        for (int s = 0; s < kAccStages; ++s) { tc::mbar_init(&S.acc_full[s], 1); tc::mbar_init(&S.acc_empty[s], kEpiWarps); }
+        tc::fence_barrier_init();
+    }
+    if (warp == 1) tc::tmem_alloc(&S.tmem_slot, 512);
+    tc::tc_fence_before();
+    __syncthreads();
+    tc::tc_fence_after();
+    const uint32_t tmem = S.tmem_slot;
+
+    if (warp == 0) {
+        // ===================================== producer =====================================
+        if (lane == 0) {
+            uint32_t b_it = 0, a_it = 0;
+            for (uint32_t pi = blockIdx.x; pi < p.n_pairs; pi += gridDim.x) {
+                const eacham_pair_t pr = p.pairs[pi];
+                const ImageDescTc A = p.images[pr.first], B = p.images[pr.second];
+                if (A.rows == 0 || B.rows == 0) continue;
+                const uint32_t na128 = (A.rows + 127) / 128, nbt = (B.rows + 127) / 128;
+                const uint8_t* Ab = p.tc_arena + A.tc_offset;
+                const uint8_t* Bb = p.tc_arena + B.tc_offset;
+                for (uint32_t ab = 0; ab * 2 < na128; ++ab, ++a_it) {
+                    const uint32_t nh = min(2u, na128 - ab * 2);
+                    tc::mbar_wait(&S.a_empty, (a_it & 1) ^ 1);
+                    tc::mbar_expect_tx(&S.a_full, nh * tc::kAOperandBytes);
+                    for (uint32_t h = 0; h < nh; ++h)
+                        tc::bulk_g2s(S.a[h], Ab + (size_t)(ab * 2 + h) * tc::kBlockBytes, tc::kAOperandBytes, &S.a_full);
+                    for (uint32_t bt = 0; bt < nbt; ++bt, ++b_it) {
+                        const uint32_t st = b_it % kBStages;
+                        tc::mbar_wait(&S.b_empty[st], ((b_it / kBStages) & 1) ^ 1);
+                        tc::mbar_expect_tx(&S.b_full[st], tc::kAOperandBytes);
+                        const uint8_t* src = Bb + (size_t)bt * tc::kBlockBytes;
+                        tc::bulk_g2s(S.b[st], src, tc::kDataBytes, &S.b_full[st]);
+                        tc::bulk_g2s(S.b[st] + tc::kDataBytes, src + tc::kDataBytes + tc::kAugBytes, tc::kAugBytes, &S.b_full[st]);
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================================== MMA issuer =====================================
+        if (lane == 0) {
+            const uint64_t dbase = tc::make_smem_desc_base(tc::kLBO, tc::kSBO);
+            const uint32_t idesc = tc::make_idesc_bf16_f32(128, 128, true);
+            uint32_t b_it = 0, a_it = 0, acc_it = 0;
+            for (uint32_t pi = blockIdx.x; pi < p.n_pairs; pi += gridDim.x) {
+                const eacham_pair_t pr = p.pairs[pi];
+                const ImageDescTc A = p.images[pr.first], B = p.images[pr.second];
+                if (A.rows == 0 || B.rows == 0) continue;
+                const uint32_t na128 = (A.rows + 127) / 128, nbt = (B.rows + 127) / 128;
+                for (uint32_t ab = 0; ab * 2 < na128; ++ab, ++a_it) {
+                    const uint32_t nh = min(2u, na128 - ab * 2);
+                    tc::mbar_wait(&S.a_full, a_it & 1);
+                    for (uint32_t bt = 0; bt < nbt; ++bt, ++b_it, ++acc_it) {
+                        const uint32_t st = b_it % kBStages, as = acc_it % kAccStages;
+                        tc::mbar_wait(&S.b_full[st], (b_it / kBStages) & 1);
+                        tc::mbar_wait(&S.acc_empty[as], ((acc_it / kAccStages) & 1) ^ 1);
+                        tc::tc_fence_after();
+                        const uint32_t b_addr = tc::smem_u32(S.b[st]);
+                        for (uint32_t h = 0; h < nh; ++h) {
+                            const uint32_t a_addr = tc::smem_u32(S.a[h]);
+                            const uint32_t d = tmem + as * 256 + h * 128;
+#pragma unroll
+                            for (int ks = 0; ks < tc::kKSteps; ++ks)
+                                tc::mma_bf16(d, tc::smem_desc(dbase, a_addr + ks * 2 * tc::kChunkStride),
+                                             tc::smem_desc(dbase, b_addr + ks * 2 * tc::kChunkStride), idesc, ks > 0);
+                        }
+                        tc::mma_commit(&S.b_empty[st]);      // B stage reusable once these MMAs have read it
+                        tc::mma_commit(&S.acc_full[as]);     // accumulators ready for the epilogue
+                    }
+                    tc::mma_commit(&S.a_empty);              // A block reusable
+                }
+            }
+        }
+    } else {
+        // ===================================== epilogue =====================================
+        const int e = warp - 2, q = warp & 3, cp = e >> 2;
+        const int et = e * 32 + lane;                         // 0..255 within the epilogue group
+        uint8_t* my_scratch = p.scratch + (size_t)blockIdx.x * tc_scratch_bytes_per_cta(p.rows_cap, p.cols_cap);
+        long long* colstate = reinterpret_cast<long long*>(my_scratch);                       // [cols_cap][2]
+        uint32_t* m12 = reinterpret_cast<uint32_t*>(my_scratch + (size_t)p.cols_cap * 16);     // [rows_cap]
+        uint32_t* m21 = m12 + p.rows_cap;                                                      // [cols_cap]
+        uint32_t acc_it = 0;
+        for (uint32_t pi = blockIdx.x; pi < p.n_pairs; pi += gridDim.x) {
+            const eacham_pair_t pr = p.pairs[pi];
+            const ImageDescTc A = p.images[pr.first], B = p.images[pr.second];
+            const uint32_t N = A.rows, M = B.rows;
+            if (N == 0 || M == 0) {
+                if (et == 0) {
+                    eacham_pair_result_t r;
+                    r.n12 = 0; r.n21 = 0; r.n_mutual = 0; r.flags = (0u < p.min_dir) ? EACHAM_PAIR_GATED : 0u; r.offset = 0; r.count = 0;
+                    p.results[pi] = r;
+                }
+                continue;
+            }
+            const float* Af = reinterpret_cast<const float*>(p.arena + A.offset);
+            const float* Bf = reinterpret_cast<const float*>(p.arena + B.offset);
+            const uint32_t na128 = (N + 127) / 128, nbt = (M + 127) / 128;
+            for (uint32_t j = et; j < nbt * 128; j += kEpiThreads) { colstate[2 * j] = kEmptyComp; colstate[2 * j + 1] = kEmptyComp; }
+            epi_bar();
+
+            for (uint32_t ab = 0; ab * 2 < na128; ++ab) {
+                const uint32_t nh = min(2u, na128 - ab * 2);
+                int32_t m0[2] = {kEmptyKeyTc, kEmptyKeyTc}, m1[2] = {kEmptyKeyTc, kEmptyKeyTc};
+                uint32_t t0[2] = {0xFFFFu, 0xFFFFu}, t1[2] = {0xFFFFu, 0xFFFFu};
+                for (uint32_t bt = 0; bt < nbt; ++bt, ++acc_it) {
+                    const uint32_t as = acc_it % kAccStages;
+                    // column state of this tile: issue the (L2) load early, consumed after the barrier
+                    long long c0 = 0, c1 = 0;
+                    if (et < 128) { c0 = colstate[2 * (bt * 128 + et)]; c1 = colstate[2 * (bt * 128 + et) + 1]; }
+                    const int32_t o00 = m0[0], o10 = m1[0], o01 = m0[1], o11 = m1[1];
+                    tc::mbar_wait(&S.acc_full[as], (acc_it / kAccStages) & 1);
+                    tc::tc_fence_after();
+                    const uint32_t taddr = tmem + as * 256 + ((uint32_t)(q * 32) << 16);
+                    uint2* slot_q = S.slots[bt & 1][q];
+                    if (nh == 2) epi_tile<2>(taddr, cp, q, lane, m0, m1, slot_q);
+                    else epi_tile<1>(taddr, cp, q, lane, m0, m1, slot_q);
+                    tc::tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) tc::mbar_arrive(&S.acc_empty[as]);       // TMEM stage free for the next MMA
+                    // coarse (tile) index of the row candidates
+#pragma unroll
+                    for (int h = 0; h < 2; ++h) {
+                        const int32_t om0 = h ? o01 : o00, om1 = h ? o11 : o10;
+                        if (m0[h] != om0) { t1[h] = (m1[h] == om0) ? t0[h] : bt; t0[h] = bt; }
+                        else if (m1[h] != om1) t1[h] = bt;
+                    }
+                    epi_bar();                                              // all 8 warps' slots of this tile are written
+                    if (et < 128) {
+                        long long g0 = kEmptyComp, g1 = kEmptyComp;
+#pragma unroll
+                        for (int qq = 0; qq < 4; ++qq) {
+                            const uint2 s = S.slots[bt & 1][qq][et];
+                            const long long k0 = ((long long)((int32_t)s.x >> 8) << 32) | (long long)(ab * kABlockRows + (s.x & 0xFFu));
+                            const long long k1 = ((long long)((int32_t)s.y >> 8) << 32) | (long long)(ab * kABlockRows + (s.y & 0xFFu));
+                            comp_merge(k0, k1, g0, g1);
+                        }
+                        comp_merge(c0, c1, g0, g1);
+                        colstate[2 * (bt * 128 + et)] = g0;
+                        colstate[2 * (bt * 128 + et) + 1] = g1;
+                    }
+                }
+                // ---- rows of this block are complete: merge the two column halves, re-rank exactly, ratio test ----
+                if (cp == 1) {
+#pragma unroll
+                    for (int h = 0; h < 2; ++h) S.rowkeys[h * 128 + q * 32 + lane] = make_int4(m0[h], m1[h], (int)t0[h], (int)t1[h]);
+                }
+                epi_bar();
+                if (cp == 0) {
+#pragma unroll
+                    for (int h = 0; h < 2; ++h) {
+                        const int4 o = S.rowkeys[h * 128 + q * 32 + lane];
+                        long long a0 = ((long long)(m0[h] >> 8) << 32) | (long long)(t0[h] * 128 + (m0[h] & 0xFF));
+                        long long a1 = ((long long)(m1[h] >> 8) << 32) | (long long)(t1[h] * 128 + (m1[h] & 0xFF));
+                        const long long b0 = ((long long)(o.x >> 8) << 32) | (long long)((uint32_t)o.z * 128 + 64 + (o.x & 0xFF));
+                        const long long b1 = ((long long)(o.y >> 8) << 32) | (long long)((uint32_t)o.w * 128 + 64 + (o.y & 0xFF));
+                        comp_merge(b0, b1, a0, a1);
+                        S.rowcand[h * 128 + q * 32 + lane] = make_uint2((uint32_t)a0, (uint32_t)a1);
+                    }
+                }
+                epi_bar();
+                for (int r = 0; r < 32; ++r) {
+                    const uint32_t lr = e * 32 + r, row = ab * kABlockRows + lr;
+                    if (row < N) {
+                        const uint2 cand = S.rowcand[lr];
+                        const uint32_t mm = rerank_ratio(Af + (size_t)row * 128, Bf, cand.x, cand.y, M, p.ratio, lane);
+                        if (lane == 0) m12[row] = mm;
+                    }
+                }
+                epi_bar();                                                  // rowkeys / rowcand reusable
+            }
+
+            // ---- columns: re-rank, ratio -> m21 ----
+            __threadfence_block();
+            for (uint32_t j = e; j < M; j += kEpiWarps) {
+                const long long k0 = colstate[2 * j], k1 = colstate[2 * j + 1];
+                const uint32_t mm = rerank_ratio(Bf + (size_t)j * 128, Af, (uint32_t)k0, (uint32_t)k1, N, p.ratio, lane);
+                if (lane == 0) m21[j] = mm;
+            }
+            __threadfence_block();
+            epi_bar();
+
+            // ---- gates, mutual filter, ordered compaction (main.cpp:111-146) ----
+            uint32_t c12 = 0, c21 = 0;
+            for (uint32_t i = et; i < N; i += kEpiThreads) c12 += m12[i] != EACHAM_NONE;
+            for (uint32_t j = et; j < M; j += kEpiThreads) c21 += m21[j] != EACHAM_NONE;
+            c12 = __reduce_add_sync(0xffffffffu, c12);
+            c21 = __reduce_add_sync(0xffffffffu, c21);
+            if (lane == 0) { S.red[e] = c12; S.red[kEpiWarps + e] = c21; }
+            epi_bar();
+            uint32_t n12 = 0, n21 = 0;
+#pragma unroll
+            for (int w = 0; w < kEpiWarps; ++w) { n12 += S.red[w]; n21 += S.red[kEpiWarps + w]; }
+            const bool gated = p.cross_check ? (n12 < p.min_dir || n21 < p.min_dir) : (n12 < p.min_dir);
+            const uint32_t per = (N + kEpiThreads - 1) / kEpiThreads;
+            const uint32_t lo = min(N, et * per), hi = min(N, lo + per);
+            uint32_t mine = 0;
+            if (!gated)
+                for (uint32_t a = lo; a < hi; ++a) {
+                    const uint32_t b = m12[a];
+                    mine += (b != EACHAM_NONE) && (!p.cross_check || m21[b] == a);
+                }
+            uint32_t incl = mine;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const uint32_t v = __shfl_up_sync(0xffffffffu, incl, o);
+                if (lane >= o) incl += v;
+            }
+            epi_bar();
+            if (lane == 31) S.red[e] = incl;
+            epi_bar();
+            uint32_t woff = 0, total = 0;
+#pragma unroll
+            for (int w = 0; w < kEpiWarps; ++w) { if (w < e) woff += S.red[w]; total += S.red[w]; }
+            const uint32_t excl = woff + incl - mine;
+            const bool connected = !gated && total > p.min_mutual;
+            const bool emit = !gated && (connected || p.emit_all) && total > 0;
+            if (et == 0) {
+                unsigned long long base = 0;
+                if (emit) base = atomicAdd(p.cursor, (unsigned long long)total);
+                S.base = base;
+                eacham_pair_result_t r;
+                r.n12 = n12; r.n21 = n21; r.n_mutual = gated ? 0u : total;
+                r.flags = (gated ? EACHAM_PAIR_GATED : 0u) | (connected ? EACHAM_PAIR_CONNECTED : 0u);
+                r.offset = base; r.count = emit ? total : 0u;
+                p.results[pi] = r;
+            }
+            epi_bar();
+            if (emit && S.base + total <= p.matches_cap) {
+                unsigned long long o = S.base + excl;
+                for (uint32_t a = lo; a < hi; ++a) {
+                    const uint32_t b = m12[a];
+                    if ((b != EACHAM_NONE) && (!p.cross_check || m21[b] == a)) {
+                        eacham_match_t mt; mt.query = a; mt.train = b;
+                        p.matches[o++] = mt;
+                    }
+                }
+            }
+            epi_bar();
+        }
+    }
+    tc::tc_fence_before();
+    __syncthreads();
+    if (warp == 1) tc::tmem_dealloc(tmem, 512);
+}
+
+}  // namespace sift
+}  // namespace eacham

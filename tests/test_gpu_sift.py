@@ -1,0 +1,111 @@
+"""GPU parity for the SIFT (128-d float, L2) path through the C ABI.
+Exact FP32 kernels (Match / knnMatch) and the tensor-core scorer + FP32 re-rank (MatchPairs).
+Bar (BASELINE.json north_star): >= 99.9 % pair-set agreement, distances within 1e-4 relative; integer-valued
+(OpenCV-shaped) descriptors are exact in bf16 x bf16 -> fp32, so those cases must agree exactly."""
+import numpy as np
+import pytest
+
+from oracle import oracle as O
+
+pytestmark = pytest.mark.gpu
+NONE = 0xFFFFFFFF
+RTOL = 1e-4
+
+
+def _ref_pair(a, b, **kw):
+    return (O.cv2_match_pair_fast if O.have_cv2() else O.c_match_pair)(a, b, **kw)
+
+
+def _agreement(pm, want):
+    """fraction of the union of both match sets on which they agree"""
+    got = set(map(tuple, pm.matches.tolist())); ref = set(map(tuple, np.asarray(want["matches"]).reshape(-1, 2).tolist()))
+    union = got | ref
+    return 1.0 if not union else len(got & ref) / len(union)
+
+
+def test_knn2_and_match_golden_exact_fp32(matcher, sift_golden):
+    for name, g in sift_golden.items():
+        for q, t, idx, dist, m in ((g["d1"], g["d2"], g["idx12"], g["dist12"], g["m12"]),
+                                   (g["d2"], g["d1"], g["idx21"], g["dist21"], g["m21"])):
+            i, s = matcher.knnMatch(q, t)
+            fin = np.isfinite(dist)
+            assert np.array_equal(np.isfinite(s), fin), name
+            if "float" in name:
+                assert (i == idx).mean() >= 0.999, name
+                np.testing.assert_allclose(s[fin], dist[fin], rtol=RTOL)
+            else:                                   # integer-valued rows: every partial sum is exact
+                assert np.array_equal(i, idx), name
+                assert np.array_equal(s[fin], dist[fin]), name
+                got = np.full(q.shape[0], NONE, np.uint32)
+                for k, v in matcher.Match(q, t).items():
+                    got[k] = v
+                assert np.array_equal(got, m), name
+
+
+def test_match_pairs_golden_tensor_core(matcher, sift_golden):
+    names, descs, pairs = [], [], []
+    for name, g in sift_golden.items():
+        names.append(name); pairs.append((len(descs), len(descs) + 1)); descs += [g["d1"], g["d2"]]
+    matcher.Upload(descs)
+    out = matcher.MatchPairs(pairs, emit_all=True)
+    for name, pm in zip(names, out):
+        g = sift_golden[name]
+        n12, n21, nm, gated, conn = g["pair"].tolist()
+        if "float" in name:
+            assert abs(pm.n12 - n12) <= 1 and abs(pm.n21 - n21) <= 1, name
+        else:
+            assert (pm.n12, pm.n21, pm.n_mutual, pm.gated, pm.connected) == (n12, n21, nm, bool(gated), bool(conn)), name
+            assert np.array_equal(pm.matches.reshape(-1, 2), g["matches"].reshape(-1, 2)), name
+
+
+@pytest.mark.parametrize("n1,n2,integer", [(1000, 1500, True), (300, 129, True), (257, 513, True), (128, 128, True), (1, 300, True),
+                                           (640, 2, True), (2048, 2048, True), (1200, 900, False), (2048, 2048, False)])
+def test_match_pairs_sizes_vs_opencv(matcher, n1, n2, integer):
+    from eacham_b200 import synth
+    n = max(n1, n2)
+    imgs = synth.sift_image_set(2, n, seed=n1 * 31 + n2, pool=int(n * 1.2) + 50, share=0.45, integer_valued=integer)
+    a, b = np.ascontiguousarray(imgs[0][:n1]), np.ascontiguousarray(imgs[1][:n2])
+    if integer and n1 > 20 and n2 > 20:
+        b[3] = b[11]; a[5] = a[2]; b[7] = a[0]          # duplicates: ties, 0/0 and d0 = 0 cases
+    matcher.Upload([a, b])
+    pm = matcher.MatchPairs([(0, 1)], emit_all=True)[0]
+    want = _ref_pair(a, b)
+    if integer:
+        assert (pm.n12, pm.n21, pm.n_mutual, pm.gated, pm.connected) == \
+            (want["n12"], want["n21"], want["n_mutual"], want["gated"], want["connected"])
+        assert np.array_equal(pm.matches.reshape(-1, 2), want["matches"].reshape(-1, 2))
+    else:
+        assert _agreement(pm, want) >= 0.999
+        assert abs(pm.n12 - want["n12"]) <= max(1, want["n12"] // 500)
+    pt = matcher.MatchPairs([(1, 0)], emit_all=True)[0]
+    assert sorted(map(tuple, pt.matches[:, ::-1].tolist())) == sorted(map(tuple, pm.matches.tolist()))
+
+
+def test_tensor_core_path_agrees_with_exact_fp32_path(matcher):
+    """Same pairs through the tcgen05 scorer and through the all-FP32 kernels (cfg flag): identical on integer-valued
+    data, >= 99.9 % on general floats."""
+    import ctypes
+    import eacham_b200
+    from eacham_b200 import synth, _lib as L
+
+    class Exact(eacham_b200.FeatureMatcherGpu):
+        def __init__(self):
+            self.inliersRatio = 0.8; self.ratio = 0.8; self.min_dir = 30; self.min_mutual = 30; self.cross_check = True
+            self._lib = L.load(); self.device = 0
+            cfg = L.Config(device=0, max_images=0, match_buffer_entries=0, flags=1)
+            h = ctypes.c_void_p(); L.check(self._lib.eacham_gpu_create(ctypes.byref(cfg), ctypes.byref(h))); self._h = h
+
+    for integer in (True, False):
+        imgs = synth.sift_image_set(4, 1536, seed=99, pool=2500, share=0.4, integer_valued=integer)
+        pairs = synth.exhaustive_pairs(4)
+        matcher.Upload(imgs)
+        tc = matcher.MatchPairs(pairs, emit_all=True)
+        with Exact() as ex:
+            ex.Upload(imgs)
+            ref = ex.MatchPairs(pairs, emit_all=True)
+        for a, b in zip(tc, ref):
+            want = dict(matches=b.matches)
+            if integer:
+                assert (a.n12, a.n21, a.n_mutual) == (b.n12, b.n21, b.n_mutual) and np.array_equal(a.matches, b.matches)
+            else:
+                assert _agreement(a, want) >= 0.999
