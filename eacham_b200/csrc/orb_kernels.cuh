@@ -90,9 +90,29 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t by
                  ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
 
+// 256-bit Hamming distance. The 8 XOR words are compressed with four carry-save adders (Harley-Seal step:
+// sum = a^b^c, carry = maj(a,b,c), one LOP3 each) into 4 bit-planes of weight 1,1,2,4, so only 4 POPC are issued
+// instead of 8:  d = popc(s2) + popc(x7) + 2*popc(s3) + 4*popc(c3).  Same integer result as Tools3d.h:46-63.
+// POPC is the scarce pipe (16 lane-ops/clk/SM); LOP3 runs at 64/clk/SM and the adds go to the FMA pipe as IMAD,
+// which is how this loop exceeds the "8 POPC per distance" roofline (tools/csa_microbench.cu).
+__device__ __forceinline__ uint32_t xor3(uint32_t a, uint32_t b, uint32_t c) {
+    uint32_t r;
+    asm("lop3.b32 %0, %1, %2, %3, 0x96;" : "=r"(r) : "r"(a), "r"(b), "r"(c));
+    return r;
+}
+__device__ __forceinline__ uint32_t maj3(uint32_t a, uint32_t b, uint32_t c) {
+    uint32_t r;
+    asm("lop3.b32 %0, %1, %2, %3, 0xE8;" : "=r"(r) : "r"(a), "r"(b), "r"(c));
+    return r;
+}
 __device__ __forceinline__ uint32_t hamming256(const uint32_t (&a)[8], const uint4& b0, const uint4& b1) {
-    return __popc(a[0] ^ b0.x) + __popc(a[1] ^ b0.y) + __popc(a[2] ^ b0.z) + __popc(a[3] ^ b0.w) +
-           __popc(a[4] ^ b1.x) + __popc(a[5] ^ b1.y) + __popc(a[6] ^ b1.z) + __popc(a[7] ^ b1.w);
+    const uint32_t x0 = a[0] ^ b0.x, x1 = a[1] ^ b0.y, x2 = a[2] ^ b0.z, x3 = a[3] ^ b0.w;
+    const uint32_t x4 = a[4] ^ b1.x, x5 = a[5] ^ b1.y, x6 = a[6] ^ b1.z, x7 = a[7] ^ b1.w;
+    const uint32_t s0 = xor3(x0, x1, x2), c0 = maj3(x0, x1, x2);
+    const uint32_t s1 = xor3(x3, x4, x5), c1 = maj3(x3, x4, x5);
+    const uint32_t s2 = xor3(s0, s1, x6), c2 = maj3(s0, s1, x6);
+    const uint32_t s3 = xor3(c0, c1, c2), c3 = maj3(c0, c1, c2);
+    return __popc(s2) + __popc(x7) + 2 * __popc(s3) + 4 * __popc(c3);
 }
 
 // top-2 of the union of two sorted pairs (keys are unique apart from kEmptyKey-class fillers)

@@ -1,0 +1,82 @@
+// Microbenchmark: 256-bit Hamming distance with carry-save compression before POPC (fewer POPC, more LOP3),
+// in the same register-tiled loop as orb_match_pairs_kernel (8 rows/thread, top-2 both directions, REDUX merge).
+// NPOPC = 8: plain; 6: two CSAs; 4: four CSAs (Harley-Seal step).
+#include <cstdio>
+#include <cstdint>
+#include <cuda_runtime.h>
+
+__device__ __forceinline__ uint32_t xor3(uint32_t a, uint32_t b, uint32_t c) { uint32_t r; asm("lop3.b32 %0, %1, %2, %3, 0x96;" : "=r"(r) : "r"(a), "r"(b), "r"(c)); return r; }
+__device__ __forceinline__ uint32_t maj3(uint32_t a, uint32_t b, uint32_t c) { uint32_t r; asm("lop3.b32 %0, %1, %2, %3, 0xE8;" : "=r"(r) : "r"(a), "r"(b), "r"(c)); return r; }
+
+template <int NPOPC>
+__device__ __forceinline__ uint32_t hamming(const uint32_t (&a)[8], const uint4& b0, const uint4& b1) {
+    const uint32_t x0 = a[0] ^ b0.x, x1 = a[1] ^ b0.y, x2 = a[2] ^ b0.z, x3 = a[3] ^ b0.w, x4 = a[4] ^ b1.x, x5 = a[5] ^ b1.y,
+                   x6 = a[6] ^ b1.z, x7 = a[7] ^ b1.w;
+    if (NPOPC == 8) return __popc(x0) + __popc(x1) + __popc(x2) + __popc(x3) + __popc(x4) + __popc(x5) + __popc(x6) + __popc(x7);
+    const uint32_t s0 = xor3(x0, x1, x2), c0 = maj3(x0, x1, x2), s1 = xor3(x3, x4, x5), c1 = maj3(x3, x4, x5);
+    if (NPOPC == 6) return __popc(s0) + __popc(s1) + __popc(x6) + __popc(x7) + 2 * (__popc(c0) + __popc(c1));
+    const uint32_t s2 = xor3(s0, s1, x6), c2 = maj3(s0, s1, x6);
+    const uint32_t s3 = xor3(c0, c1, c2), c3 = maj3(c0, c1, c2);
+    return __popc(s2) + __popc(x7) + 2 * __popc(s3) + 4 * __popc(c3);
+}
+
+template <int NPOPC>
+__global__ void __launch_bounds__(512, 1) mix(uint32_t* out, long long* cycles, uint32_t seed, int ncols) {
+    __shared__ uint4 cols[2 * 256];
+    for (int i = threadIdx.x; i < 512; i += blockDim.x) { uint32_t v = seed * (i + 7); cols[i] = make_uint4(v, v * 3, v * 5, v * 7); }
+    uint32_t a[8][8];
+#pragma unroll
+    for (int r = 0; r < 8; ++r)
+#pragma unroll
+        for (int w = 0; w < 8; ++w) a[r][w] = seed * (threadIdx.x * 64 + r * 8 + w + 1);
+    uint32_t m0[8], m1[8];
+#pragma unroll
+    for (int r = 0; r < 8; ++r) { m0[r] = 0xffffffffu; m1[r] = 0xffffffffu; }
+    uint32_t acc = 0;
+    __syncthreads();
+    long long t0 = clock64();
+#pragma unroll 1
+    for (int j = 0; j < ncols; ++j) {
+        uint4 b0 = cols[(j & 255) * 2], b1 = cols[(j & 255) * 2 + 1];
+        uint32_t c0 = 0xffffffffu, c1 = 0xffffffffu;
+#pragma unroll
+        for (int r = 0; r < 8; ++r) {
+            uint32_t d = hamming<NPOPC>(a[r], b0, b1);
+            uint32_t kr = (d << 16) + j, kc = (d << 16) + r * 512;
+            m1[r] = min(m1[r], max(m0[r], kr)); m0[r] = min(m0[r], kr);
+            c1 = min(c1, max(c0, kc)); c0 = min(c0, kc);
+        }
+        uint32_t g0 = __reduce_min_sync(0xffffffffu, c0);
+        uint32_t x = (c0 == g0) ? c1 : c0;
+        uint32_t g1 = __reduce_min_sync(0xffffffffu, x);
+        acc += g0 ^ g1;
+    }
+    long long t1 = clock64();
+    uint32_t s = acc;
+#pragma unroll
+    for (int r = 0; r < 8; ++r) s += m0[r] ^ m1[r];
+    out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+    if (threadIdx.x == 0) cycles[blockIdx.x] = t1 - t0;
+}
+
+template <int NPOPC>
+void run(uint32_t* out, long long* cyc, int nsm) {
+    for (int rep = 0; rep < 2; ++rep) {
+        mix<NPOPC><<<nsm, 512>>>(out, cyc, 977u, 4096);
+        cudaDeviceSynchronize();
+        long long h[256]; cudaMemcpy(h, cyc, sizeof(long long) * nsm, cudaMemcpyDeviceToHost);
+        long long mx = 0; for (int i = 0; i < nsm; ++i) mx = h[i] > mx ? h[i] : mx;
+        double dists = 512.0 * 8 * 4096;
+        if (rep) printf("{\"op\": \"orb_inner_loop_csa\", \"popc_per_distance\": %d, \"distances_per_clk_per_sm\": %.3f, \"equiv_popc8_per_clk_per_sm\": %.2f, \"cycles\": %lld}\n",
+                        NPOPC, dists / mx, 8 * dists / mx, mx);
+    }
+}
+
+int main() {
+    cudaDeviceProp p; cudaGetDeviceProperties(&p, 0);
+    int nsm = p.multiProcessorCount;
+    uint32_t* out; long long* cyc;
+    cudaMalloc(&out, sizeof(uint32_t) * nsm * 512); cudaMalloc(&cyc, sizeof(long long) * 256);
+    run<8>(out, cyc, nsm); run<6>(out, cyc, nsm); run<4>(out, cyc, nsm);
+    return 0;
+}
