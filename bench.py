@@ -315,11 +315,19 @@ def main():
             achieved = work_per_pair * (len(my_pairs) * args.steps) / (float(sum(kernel_ms)) * 1e-3)
             traffic_path = os.path.join(ROOT, "profiles", "traffic.json")
             traffic = json.load(open(traffic_path)).get(args.workload) if os.path.exists(traffic_path) else None
+            alu_ops_per_distance = 22.0        # 16 LOP3 + 6 VIMNMX issued on the ALU pipe per distance (SASS count)
+            alu_peak = sm_count * 64.0 * pk["sm_max_mhz"] * 1e6
+            alu_achieved = alu_ops_per_distance * n_desc * n_desc * (len(my_pairs) * args.steps) / (float(sum(kernel_ms)) * 1e-3)
             roof = {"bound": "int_popc", "achieved": achieved / 1e12, "peak": peak / 1e12, "unit": "TPOPC32/s",
                     "frac": achieved / peak, "traffic": traffic,
                     "peak_source": f"16.00 POPC lane-ops/clk/SM measured (profiles/r01_pipe_microbench.jsonl) x 148 SMs x sm_max_mhz "
                                    f"{pk['sm_max_mhz']:.0f} ({pk['_source']})",
                     "work_per_pair": work_per_pair, "kernel": "orb_match_pairs_kernel",
+                    "note": "algorithmic work = 8 POPC32 per 256-bit distance, distance matrix evaluated once per pair (SURVEY.md 8(d)). "
+                            "frac > 1 is real: the kernel compresses the 8 XOR words with carry-save adders and issues 4 POPC per distance, "
+                            "so the POPC pipe is no longer the limiter; the ALU pipe (LOP3 + VIMNMX) is -- see alu_pipe.",
+                    "alu_pipe": {"achieved_tlaneops": alu_achieved / 1e12, "peak_tlaneops": alu_peak / 1e12, "frac": alu_achieved / alu_peak,
+                                 "ops_per_distance": alu_ops_per_distance, "peak_source": "64 lane-ops/clk/SM (LOP3 63.2 measured) x 148 x sm_max_mhz"},
                     "hbm": {"achieved_gbs": 2 * n_desc * 32 * len(my_pairs) * args.steps / (float(sum(kernel_ms)) * 1e-3) / 1e9,
                             "peak_gbs": pk["hbm_gbs"], "note": "algorithmic bytes = both images of every pair; far from the HBM bound"}}
         else:

@@ -73,10 +73,10 @@ __global__ void __launch_bounds__(256) sift_prep_kernel(const float* __restrict_
 // =============================================================================================================
 // The fused SIFT pair kernel.
 //
-// One persistent CTA per image pair (static round-robin over the pair list). 320 threads:
+// One persistent CTA per image pair (static round-robin over the pair list). 576 threads:
 //   warp 0    producer: 1-D bulk copies (TMA engine) of pre-tiled bf16 blocks, mbarrier pipeline
 //   warp 1    MMA issuer: one thread issues tcgen05.mma (M=128, N=128, K=16) x 9 k-steps x 2 row halves per tile
-//   warps 2-9 epilogue: tcgen05.ld -> packed-key top-2 for rows (registers) and columns (REDUX + smem slots)
+//   warps 2-17 epilogue: tcgen05.ld -> packed-key top-2 for rows (registers) and columns (REDUX + smem slots)
 // A block of 256 rows of the first image stays in shared memory while the second image streams through in
 // 128-column tiles (3 stages). Accumulators: 2 stages x 2 halves x 128 fp32 columns = all 512 TMEM columns, so the
 // tensor core fills stage s+1 while the epilogue drains stage s.
@@ -111,7 +111,9 @@ struct PairParamsTc {
     uint32_t rows_cap, cols_cap;    // multiples of 128
 };
 
-constexpr int kEpiWarps = 8;
+constexpr int kEpiWarps = 16;          // 4 per TMEM lane quadrant, 32 columns of every tile each
+constexpr int kColParts = kEpiWarps / 4;
+constexpr int kColsPerWarp = 128 / kColParts;
 constexpr int kEpiThreads = kEpiWarps * 32;
 constexpr int kThreadsTc = 64 + kEpiThreads;
 constexpr int kBStages = 3;
@@ -128,7 +130,7 @@ struct SmemTc {
     uint8_t a[2][tc::kAOperandBytes];
     uint8_t b[kBStages][tc::kAOperandBytes];
     uint2 slots[2][4][128];
-    int4 rowkeys[kABlockRows];          // cp=1 partial row state: m0, m1, t0, t1
+    int4 rowkeys[kColParts - 1][kABlockRows];   // partial row state of column parts 1..: m0, m1, t0, t1
     uint2 rowcand[kABlockRows];         // merged candidates j0, j1
     uint64_t b_full[kBStages], b_empty[kBStages], a_full, a_empty, acc_full[kAccStages], acc_empty[kAccStages];
     uint32_t tmem_slot;
@@ -169,35 +171,44 @@ __device__ __forceinline__ uint32_t rerank_ratio(const float* __restrict__ qrow,
     return ((double)__fdiv_rn(d0, d1) < ratio) ? j0 : EACHAM_NONE;
 }
 
+// key = (value bits & 0xFFFFFF00) | index byte, as ONE LOP3 ((a & b) | c, LUT 0xEA)
+__device__ __forceinline__ int32_t make_key(uint32_t v, uint32_t mask, uint32_t idx) {
+    uint32_t r;
+    asm("lop3.b32 %0, %1, %2, %3, 0xEA;" : "=r"(r) : "r"(v), "r"(mask), "r"(idx));
+    return (int32_t)r;
+}
+
 template <int NH>
 __device__ __forceinline__ void epi_tile(uint32_t acc_taddr, int cp, int q, int lane, int32_t (&m0)[2], int32_t (&m1)[2],
                                          uint2* __restrict__ slot_q) {
     const uint32_t ridx0 = q * 32 + lane, ridx1 = 128 + q * 32 + lane;
+    uint32_t mask = 0xFFFFFF00u;
+    asm volatile("" : "+r"(mask));                       // keep the mask in a register so both keys are single LOP3s
 #pragma unroll
-    for (int ch = 0; ch < 4; ++ch) {
+    for (int ch = 0; ch < kColsPerWarp / 16; ++ch) {
         uint32_t v0[16], v1[16];
-        tc::tmem_ld16(acc_taddr + cp * 64 + ch * 16, v0);
-        if (NH == 2) tc::tmem_ld16(acc_taddr + 128 + cp * 64 + ch * 16, v1);
+        tc::tmem_ld16(acc_taddr + cp * kColsPerWarp + ch * 16, v0);
+        if (NH == 2) tc::tmem_ld16(acc_taddr + 128 + cp * kColsPerWarp + ch * 16, v1);
         tc::tmem_ld_wait();
 #pragma unroll
         for (int k = 0; k < 16; ++k) {
             const uint32_t idx = ch * 16 + k;
-            const int32_t kr0 = (int32_t)((v0[k] & 0xFFFFFF00u) | idx);
+            const int32_t kr0 = make_key(v0[k], mask, idx);
             m1[0] = min(m1[0], max(m0[0], kr0));
             m0[0] = min(m0[0], kr0);
-            int32_t lo = (int32_t)((v0[k] & 0xFFFFFF00u) | ridx0), hi = kEmptyKeyTc;
+            int32_t lo = make_key(v0[k], mask, ridx0), hi = kEmptyKeyTc;
             if (NH == 2) {
-                const int32_t kr1 = (int32_t)((v1[k] & 0xFFFFFF00u) | idx);
+                const int32_t kr1 = make_key(v1[k], mask, idx);
                 m1[1] = min(m1[1], max(m0[1], kr1));
                 m0[1] = min(m0[1], kr1);
-                const int32_t kc1 = (int32_t)((v1[k] & 0xFFFFFF00u) | ridx1);
+                const int32_t kc1 = make_key(v1[k], mask, ridx1);
                 hi = max(lo, kc1);
                 lo = min(lo, kc1);
             }
             const int32_t g0 = __reduce_min_sync(0xffffffffu, lo);
             const int32_t x = (lo == g0) ? hi : lo;
             const int32_t g1 = __reduce_min_sync(0xffffffffu, x);
-            if (lane == (int)(idx & 31)) slot_q[cp * 64 + idx] = make_uint2((uint32_t)g0, (uint32_t)g1);
+            slot_q[cp * kColsPerWarp + idx] = make_uint2((uint32_t)g0, (uint32_t)g1);   // warp-uniform value: all lanes store the same word
         }
     }
 }
@@ -351,26 +362,29 @@ __global__ void __launch_bounds__(kThreadsTc, 1) sift_match_pairs_kernel(const P
                     }
                 }
                 // ---- rows of this block are complete: merge the two column halves, re-rank exactly, ratio test ----
-                if (cp == 1) {
+                if (cp > 0) {
 #pragma unroll
-                    for (int h = 0; h < 2; ++h) S.rowkeys[h * 128 + q * 32 + lane] = make_int4(m0[h], m1[h], (int)t0[h], (int)t1[h]);
+                    for (int h = 0; h < 2; ++h) S.rowkeys[cp - 1][h * 128 + q * 32 + lane] = make_int4(m0[h], m1[h], (int)t0[h], (int)t1[h]);
                 }
                 epi_bar();
                 if (cp == 0) {
 #pragma unroll
                     for (int h = 0; h < 2; ++h) {
-                        const int4 o = S.rowkeys[h * 128 + q * 32 + lane];
                         long long a0 = ((long long)(m0[h] >> 8) << 32) | (long long)(t0[h] * 128 + (m0[h] & 0xFF));
                         long long a1 = ((long long)(m1[h] >> 8) << 32) | (long long)(t1[h] * 128 + (m1[h] & 0xFF));
-                        const long long b0 = ((long long)(o.x >> 8) << 32) | (long long)((uint32_t)o.z * 128 + 64 + (o.x & 0xFF));
-                        const long long b1 = ((long long)(o.y >> 8) << 32) | (long long)((uint32_t)o.w * 128 + 64 + (o.y & 0xFF));
-                        comp_merge(b0, b1, a0, a1);
+#pragma unroll
+                        for (int c = 1; c < kColParts; ++c) {
+                            const int4 o = S.rowkeys[c - 1][h * 128 + q * 32 + lane];
+                            const long long b0 = ((long long)(o.x >> 8) << 32) | (long long)((uint32_t)o.z * 128 + c * kColsPerWarp + (o.x & 0xFF));
+                            const long long b1 = ((long long)(o.y >> 8) << 32) | (long long)((uint32_t)o.w * 128 + c * kColsPerWarp + (o.y & 0xFF));
+                            comp_merge(b0, b1, a0, a1);
+                        }
                         S.rowcand[h * 128 + q * 32 + lane] = make_uint2((uint32_t)a0, (uint32_t)a1);
                     }
                 }
                 epi_bar();
-                for (int r = 0; r < 32; ++r) {
-                    const uint32_t lr = e * 32 + r, row = ab * kABlockRows + lr;
+                for (int r = 0; r < kABlockRows / kEpiWarps; ++r) {
+                    const uint32_t lr = e * (kABlockRows / kEpiWarps) + r, row = ab * kABlockRows + lr;
                     if (row < N) {
                         const uint2 cand = S.rowcand[lr];
                         const uint32_t mm = rerank_ratio(Af + (size_t)row * 128, Bf, cand.x, cand.y, M, p.ratio, lane);
