@@ -293,15 +293,19 @@ def main():
             m.Upload(images)
         else:
             D.upload_and_broadcast(m, images, src=0)
-        res, buf = m.MatchPairsRaw(my_pairs)
-        if dist is not None:
-            D.gather_results(res, buf, n_pairs, dst=0)
+        if dist is None:
+            res, buf = m.MatchPairsRaw(my_pairs)                      # host buffers in, host buffers out
+        else:
+            m.MatchPairsDevice(my_pairs)                              # shard stays in HBM ...
+            got = D.gather_results_device(m, n_pairs, dst=0)          # ... NVLink gather, one D2H on rank 0
+            if rank == 0:
+                res, buf = got
         barrier()
         dt = max_over_ranks(time.perf_counter() - t0)
         if s > 0:
             e2e_s += dt
             h2d = arena_bytes + my_pairs.nbytes
-            d2h = res.nbytes + buf.nbytes
+            d2h = (res.nbytes + buf.nbytes) if rank == 0 else 0
     e2e_value = n_pairs * e2e_steps / e2e_s
 
     if rank == 0:
@@ -363,7 +367,7 @@ def main():
             "e2e": {"value": e2e_value, "unit": "pairs/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                     "steps": e2e_steps, "includes": "set_descriptors + commit (pinned staging, one H2D)" +
                     (" + NCCL arena broadcast" if world > 1 else "") + " + pair list H2D + kernel + D2H of results and matches" +
-                    (" + gather to rank 0" if world > 1 else "")},
+                    (" (shards gathered to rank 0 over NVLink, one D2H there)" if world > 1 else "")},
             "gpu_launches": int(launches),
             "roofline": roof,
             "cpu_baseline": cpu,

@@ -40,7 +40,7 @@ SYMBOLS = [
     "eacham_gpu_abi_version", "eacham_gpu_device_count", "eacham_gpu_last_error", "eacham_gpu_default_opts",
     "eacham_gpu_create", "eacham_gpu_destroy", "eacham_gpu_set_descriptors", "eacham_gpu_reserve", "eacham_gpu_commit",
     "eacham_gpu_clear", "eacham_gpu_arena", "eacham_gpu_image_info", "eacham_gpu_match", "eacham_gpu_knn2",
-    "eacham_gpu_match_pairs", "eacham_gpu_match_pairs_device", "eacham_gpu_fetch_results", "eacham_gpu_last_timing",
+    "eacham_gpu_match_pairs", "eacham_gpu_match_pairs_device", "eacham_gpu_fetch_results", "eacham_gpu_device_results", "eacham_gpu_last_timing",
     "eacham_gpu_flush_l2",
 ]
 
@@ -83,6 +83,7 @@ def load() -> ctypes.CDLL:
     lib.eacham_gpu_match_pairs.argtypes = [vp, vp, sz, P(MatchOpts), vp, vp, sz, P(sz)]
     lib.eacham_gpu_match_pairs_device.argtypes = [vp, vp, sz, P(MatchOpts), P(sz)]
     lib.eacham_gpu_fetch_results.argtypes = [vp, vp, sz, vp, sz, P(sz)]
+    lib.eacham_gpu_device_results.argtypes = [vp, P(vp), P(vp), P(sz), P(sz)]
     lib.eacham_gpu_last_timing.argtypes = [vp, P(Timing)]
     lib.eacham_gpu_flush_l2.argtypes = [vp, sz]
     for name in SYMBOLS:

@@ -622,6 +622,16 @@ int eacham_gpu_fetch_results(eacham_gpu_handle* h, eacham_pair_result_t* res, si
     return fetch(h, res, n_pairs, buf, buf_cap, buf_used);
 }
 
+int eacham_gpu_device_results(eacham_gpu_handle* h, void** results, void** matches, size_t* n_pairs, size_t* n_matches) {
+    if (!h) return fail(EACHAM_ERR_INVALID_ARG, "null handle");
+    std::lock_guard<std::mutex> lk(h->mu);
+    if (results) *results = h->d_results.p;
+    if (matches) *matches = h->d_matches.p;
+    if (n_pairs) *n_pairs = h->last_n_pairs;
+    if (n_matches) *n_matches = (size_t)h->last_total;
+    return EACHAM_OK;
+}
+
 int eacham_gpu_match_pairs(eacham_gpu_handle* h, const eacham_pair_t* pairs, size_t n_pairs, const eacham_match_opts* opts,
                            eacham_pair_result_t* res, eacham_match_t* buf, size_t buf_cap, size_t* buf_used) {
     if (!h || (n_pairs && (!pairs || !res)) || (buf_cap && !buf)) return fail(EACHAM_ERR_INVALID_ARG, "null argument");

@@ -118,3 +118,43 @@ def gather_results(res: np.ndarray, matches: np.ndarray, n_pairs_total: int, dst
         base += nm
         per_res.append(rr); per_m.append(mm)
     return unshard(per_res, n_pairs_total), np.concatenate(per_m) if per_m else np.zeros(0, L.MATCH_DTYPE)
+
+
+def gather_results_device(matcher, n_pairs_total: int, dst: int = 0, group=None) -> Optional[Tuple[np.ndarray, np.ndarray]]:
+    """Same as gather_results, but straight from the device-resident outputs of the last MatchPairsDevice call:
+    shards travel GPU -> GPU over NVLink (NCCL gather) and only ``dst`` does one D2H copy."""
+    import torch
+    import torch.distributed as dist
+    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    dev = f"cuda:{matcher.device}"
+    rptr, mptr, n_res, n_m = matcher.device_results()
+    rs, ms = np.dtype(L.RESULT_DTYPE).itemsize, np.dtype(L.MATCH_DTYPE).itemsize
+    sizes = torch.tensor([n_res, n_m], dtype=torch.int64, device=dev)
+    all_sizes = [torch.zeros(2, dtype=torch.int64, device=dev) for _ in range(world)]
+    dist.all_gather(all_sizes, sizes, group=group)
+    all_sizes = [t.cpu().tolist() for t in all_sizes]
+    max_r = max(1, max(x[0] for x in all_sizes)); max_m = max(1, max(x[1] for x in all_sizes))
+    tr = torch.zeros(max_r * rs, dtype=torch.uint8, device=dev)
+    tm = torch.empty(max_m * ms, dtype=torch.uint8, device=dev)
+    if n_res:
+        tr[: n_res * rs] = torch.as_tensor(_CudaBytes(rptr, n_res * rs), device=dev)
+    if n_m:
+        tm[: n_m * ms] = torch.as_tensor(_CudaBytes(mptr, n_m * ms), device=dev)
+    gr = [torch.empty_like(tr) for _ in range(world)] if rank == dst else None
+    gm = [torch.empty_like(tm) for _ in range(world)] if rank == dst else None
+    dist.gather(tr, gr, dst=dst, group=group)
+    dist.gather(tm, gm, dst=dst, group=group)
+    if rank != dst:
+        return None
+    res_dev = torch.cat([gr[r][: all_sizes[r][0] * rs] for r in range(world)])
+    m_dev = torch.cat([gm[r][: all_sizes[r][1] * ms] for r in range(world)])
+    res_all = res_dev.cpu().numpy().view(L.RESULT_DTYPE).copy()
+    m_all = m_dev.cpu().numpy().view(L.MATCH_DTYPE)
+    per_res, pos, base = [], 0, 0
+    for r in range(world):
+        nr, nm = all_sizes[r]
+        rr = res_all[pos: pos + nr]
+        rr["offset"] += base
+        per_res.append(rr)
+        pos += nr; base += nm
+    return unshard(per_res, n_pairs_total), m_all

@@ -212,6 +212,12 @@ class FeatureMatcherGpu:
                                                    buf.ctypes.data_as(ctypes.c_void_p), buf.shape[0], ctypes.byref(used)))
         return res, buf[:used.value]
 
+    def device_results(self) -> Tuple[int, int, int, int]:
+        """(results_ptr, matches_ptr, n_pairs, n_matches) of the last batch, device resident."""
+        r = ctypes.c_void_p(); m = ctypes.c_void_p(); n = ctypes.c_size_t(); k = ctypes.c_size_t()
+        L.check(self._lib.eacham_gpu_device_results(self._h, ctypes.byref(r), ctypes.byref(m), ctypes.byref(n), ctypes.byref(k)))
+        return int(r.value or 0), int(m.value or 0), int(n.value), int(k.value)
+
     def timing(self) -> Dict[str, float]:
         t = L.Timing()
         L.check(self._lib.eacham_gpu_last_timing(self._h, ctypes.byref(t)))

@@ -161,6 +161,10 @@ EACHAM_API int eacham_gpu_match_pairs_device(eacham_gpu_handle* h, const eacham_
 EACHAM_API int eacham_gpu_fetch_results(eacham_gpu_handle* h, eacham_pair_result_t* res, size_t n_pairs, eacham_match_t* buf,
                              size_t buf_cap, size_t* buf_used);
 
+/* Device addresses of the last batch's outputs (results[n_pairs], matches[n_matches]); valid until the next
+ * match_pairs call on this handle. Lets the plumbing layer gather shards over NVLink without a host round trip. */
+EACHAM_API int eacham_gpu_device_results(eacham_gpu_handle* h, void** results, void** matches, size_t* n_pairs, size_t* n_matches);
+
 EACHAM_API int eacham_gpu_last_timing(eacham_gpu_handle* h, eacham_gpu_timing* t);
 /* Write `bytes` of device memory (L2 flush between timed benchmark iterations). */
 EACHAM_API int eacham_gpu_flush_l2(eacham_gpu_handle* h, size_t bytes);

@@ -76,3 +76,21 @@ def test_synth_is_deterministic_and_shaped():
     s = synth.sift_image_set(2, 64, seed=3, pool=100)
     assert s[0].shape == (64, 128) and s[0].dtype == np.float32 and np.array_equal(s[0], np.rint(s[0]))
     assert 400 < np.linalg.norm(s[0], axis=1).mean() < 620
+
+
+def test_match_graph_roundtrip(tmp_path):
+    from eacham_b200 import graph_io, _lib as L
+    pairs = np.array([[0, 1], [0, 2], [1, 2]], np.uint32)
+    res = np.zeros(3, L.RESULT_DTYPE)
+    res[0] = (40, 41, 35, L.PAIR_CONNECTED, 0, 35); res[1] = (3, 50, 0, L.PAIR_GATED, 0, 0); res[2] = (31, 31, 31, L.PAIR_CONNECTED, 35, 31)
+    m = np.zeros(66, L.MATCH_DTYPE); m["query"] = np.arange(66); m["train"] = np.arange(66)[::-1]
+    p = str(tmp_path / "g.bin")
+    graph_io.save_match_graph(p, pairs, res, m, n_images=3)
+    p2, r2, m2, n = graph_io.load_match_graph(p)
+    assert np.array_equal(p2, pairs) and np.array_equal(r2, res) and np.array_equal(m2, m) and n == 3
+    edges = list(graph_io.connected_edges(p2, r2, m2))
+    assert [(e[0], e[1], len(e[2])) for e in edges] == [(0, 1, 35), (1, 2, 31)]
+    assert edges[0][3][65] == 0                      # best21 is the inverse map
+    with pytest.raises(ValueError):
+        res_bad = res.copy(); res_bad[2]["count"] = 99
+        graph_io.save_match_graph(p, pairs, res_bad, m)
