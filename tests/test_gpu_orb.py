@@ -188,3 +188,48 @@ def test_cpp_shim_program():
     env = dict(os.environ, LD_LIBRARY_PATH=os.path.join(root, "eacham_b200") + ":" + os.environ.get("LD_LIBRARY_PATH", ""))
     r = subprocess.run([exe], env=env, capture_output=True, text=True, timeout=300)
     assert r.returncode == 0, r.stdout + r.stderr
+
+
+def test_images_beyond_fused_limit_use_gpu_fallback(matcher):
+    """More than 16,384 descriptors per image exceeds the fused kernel's shared-memory budget: the library switches to
+    its per-pair exact GPU kernels (never to the CPU) and the answer is unchanged."""
+    rng = np.random.default_rng(17)
+    a, b = cases.planted_pair(rng, 17000, 700, 80, dup_filler=False)
+    matcher.Upload([a, b])
+    for pair in ((0, 1), (1, 0)):
+        pm = matcher.MatchPairs([pair], emit_all=True)[0]
+        x, y = (a, b) if pair == (0, 1) else (b, a)
+        _assert_pair_equal(pm, O.c_match_pair(x, y), str(pair))
+
+
+def test_window_pairs_kitti_shape(matcher):
+    """BASELINE config 4 shape, scaled down: a frame sequence whose neighbours overlap, sliding-window pair list."""
+    from eacham_b200 import synth
+    imgs = synth.orb_image_set(40, 2048, seed=4, pool=12000, window=4000)
+    pairs = synth.window_pairs(len(imgs), 5)
+    matcher.Upload(imgs)
+    out = matcher.MatchPairs(pairs, emit_all=True)
+    ref = O.cv2_match_pair_fast if O.have_cv2() else O.c_match_pair
+    rng = np.random.default_rng(0)
+    for k in rng.choice(len(pairs), size=40, replace=False):
+        i, j = pairs[k].tolist()
+        _assert_pair_equal(out[k], ref(imgs[i], imgs[j]), f"frames {i},{j}")
+    near = [pm.n_mutual for pm in out if pm.second - pm.first == 1]
+    far = [pm.n_mutual for pm in out if pm.second - pm.first == 5]
+    assert np.mean(near) > np.mean(far)                 # neighbouring frames share more landmarks
+
+
+def test_match_graph_dump_roundtrip_from_gpu(matcher, tmp_path):
+    from eacham_b200 import synth, graph_io
+    imgs = synth.orb_image_set(6, 1024, seed=8, pool=2500)
+    pairs = synth.exhaustive_pairs(6)
+    matcher.Upload(imgs)
+    res, buf = matcher.MatchPairsRaw(pairs)
+    p = str(tmp_path / "graph.bin")
+    graph_io.save_match_graph(p, pairs, res, buf, n_images=6)
+    p2, r2, m2, n = graph_io.load_match_graph(p)
+    assert np.array_equal(r2, res) and np.array_equal(m2, buf) and n == 6
+    edges = {(i, j): b12 for i, j, b12, _ in graph_io.connected_edges(p2, r2, m2)}
+    for (i, j), b12 in edges.items():
+        assert b12 == {int(a): int(b) for a, b in O.c_match_pair(imgs[i], imgs[j])["matches"]}
+    assert len(edges) > 0

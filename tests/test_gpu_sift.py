@@ -109,3 +109,30 @@ def test_tensor_core_path_agrees_with_exact_fp32_path(matcher):
                 assert (a.n12, a.n21, a.n_mutual) == (b.n12, b.n21, b.n_mutual) and np.array_equal(a.matches, b.matches)
             else:
                 assert _agreement(a, want) >= 0.999
+
+
+def test_sift_empty_and_tiny_images(matcher):
+    from eacham_b200 import synth
+    a = synth.sift_image_set(1, 200, seed=1, pool=300)[0]
+    empty = np.zeros((0, 128), np.float32)
+    matcher.Upload([a, empty, a[:1].copy(), a[:2].copy()])
+    out = matcher.MatchPairs([(0, 1), (1, 0), (0, 2), (2, 0), (0, 3), (1, 1)], emit_all=True)
+    for pm, (x, y) in zip(out, [(a, empty), (empty, a), (a, a[:1]), (a[:1], a), (a, a[:2]), (empty, empty)]):
+        want = _ref_pair(x, y)
+        assert (pm.n12, pm.n21, pm.n_mutual, pm.gated, pm.connected) == (want["n12"], want["n21"], want["n_mutual"], want["gated"], want["connected"])
+    assert matcher.Match(a, empty) == {} and matcher.Match(empty, a) == {}
+
+
+def test_sift_full_size_properties(matcher):
+    """BASELINE config-3 shape (8k SIFT per image): an image against a row-permuted copy of itself returns the
+    permutation for every row (size-independent property; no CPU oracle needed at this size)."""
+    from eacham_b200 import synth
+    img = synth.sift_image_set(1, 8192, seed=3, pool=40000)[0]
+    img = np.unique(img, axis=0)                    # drop exact duplicate rows so that every row has one zero-distance partner
+    n = img.shape[0]
+    perm = np.random.default_rng(3).permutation(n)
+    matcher.Upload([img, np.ascontiguousarray(img[perm])])
+    pm = matcher.MatchPairs([(0, 1)], emit_all=True)[0]
+    inv = np.empty(n, np.int64); inv[perm] = np.arange(n)
+    assert pm.n12 == n and pm.n21 == n and pm.n_mutual == n
+    assert np.array_equal(pm.matches[:, 0], np.arange(n)) and np.array_equal(pm.matches[:, 1], inv)
