@@ -146,10 +146,19 @@ def gather_results_device(matcher, n_pairs_total: int, dst: int = 0, group=None)
     dist.gather(tm, gm, dst=dst, group=group)
     if rank != dst:
         return None
-    res_dev = torch.cat([gr[r][: all_sizes[r][0] * rs] for r in range(world)])
-    m_dev = torch.cat([gm[r][: all_sizes[r][1] * ms] for r in range(world)])
-    res_all = res_dev.cpu().numpy().view(L.RESULT_DTYPE).copy()
-    m_all = m_dev.cpu().numpy().view(L.MATCH_DTYPE)
+    # one D2H per array, into pinned host memory, each rank's valid prefix copied straight to its final position
+    tot_r = sum(x[0] for x in all_sizes) * rs; tot_m = sum(x[1] for x in all_sizes) * ms
+    host_r = torch.empty(max(tot_r, 1), dtype=torch.uint8, pin_memory=True)
+    host_m = torch.empty(max(tot_m, 1), dtype=torch.uint8, pin_memory=True)
+    pr = pm = 0
+    for r in range(world):
+        nr, nm = all_sizes[r][0] * rs, all_sizes[r][1] * ms
+        host_r[pr: pr + nr].copy_(gr[r][:nr], non_blocking=True)
+        host_m[pm: pm + nm].copy_(gm[r][:nm], non_blocking=True)
+        pr += nr; pm += nm
+    torch.cuda.synchronize(matcher.device)
+    res_all = host_r[:tot_r].numpy().view(L.RESULT_DTYPE).copy()
+    m_all = host_m[:tot_m].numpy().view(L.MATCH_DTYPE)
     per_res, pos, base = [], 0, 0
     for r in range(world):
         nr, nm = all_sizes[r]
