@@ -308,6 +308,20 @@ def main():
             d2h = (res.nbytes + buf.nbytes) if rank == 0 else 0
     e2e_value = n_pairs * e2e_steps / e2e_s
 
+    # ---- the reference-shaped per-call route: Match(d1, d2) one direction at a time ----
+    match_api = None
+    if rank == 0 and world == 1:
+        n_calls = 128 if kind == "orb" else 16
+        m.Match(images[0], images[1])
+        t0 = time.perf_counter()
+        for c in range(n_calls):
+            i, j = c % (n_images - 1), (c % (n_images - 1)) + 1
+            m.Match(images[i], images[j]) if c % 2 == 0 else m.Match(images[j], images[i])
+        dt = time.perf_counter() - t0
+        match_api = {"calls_per_s": n_calls / dt, "pairs_per_s": n_calls / dt / 2, "calls": n_calls,
+                     "note": "eacham_gpu_match: host descriptors in, ratio-filtered map out, per call (upload + 2 kernels + D2H); "
+                             "the drop-in for FeatureMatcherFlann::Match with the reference's own loop"}
+
     if rank == 0:
         pk = peaks()
         res_all, buf_all = res, buf
@@ -373,7 +387,8 @@ def main():
             "cpu_baseline": cpu,
             "clocks": clocks,
             "upload_ms": upload_ms, "arena_bytes": int(arena_bytes), "wall_s_timed_region": wall_s,
-            "matches_per_step": int(res_all["count"].sum()) if world == 1 else None,
+            "matches_per_step": int(res_all["count"].sum()),
+            "match_api": match_api,
         }
         print(json.dumps(line))
     m.close()
