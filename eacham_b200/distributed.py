@@ -120,6 +120,19 @@ def gather_results(res: np.ndarray, matches: np.ndarray, n_pairs_total: int, dst
     return unshard(per_res, n_pairs_total), np.concatenate(per_m) if per_m else np.zeros(0, L.MATCH_DTYPE)
 
 
+_PINNED = {}
+
+
+def _pinned(tag: str, nbytes: int):
+    """Reusable pinned host buffer (cudaHostAlloc of ~1 GB costs more than the copy it serves)."""
+    import torch
+    buf = _PINNED.get(tag)
+    if buf is None or buf.numel() < nbytes:
+        buf = torch.empty(max(int(nbytes * 1.25), 1 << 20), dtype=torch.uint8, pin_memory=True)
+        _PINNED[tag] = buf
+    return buf
+
+
 def gather_results_device(matcher, n_pairs_total: int, dst: int = 0, group=None) -> Optional[Tuple[np.ndarray, np.ndarray]]:
     """Same as gather_results, but straight from the device-resident outputs of the last MatchPairsDevice call:
     shards travel GPU -> GPU over NVLink (NCCL gather) and only ``dst`` does one D2H copy."""
@@ -148,8 +161,8 @@ def gather_results_device(matcher, n_pairs_total: int, dst: int = 0, group=None)
         return None
     # one D2H per array, into pinned host memory, each rank's valid prefix copied straight to its final position
     tot_r = sum(x[0] for x in all_sizes) * rs; tot_m = sum(x[1] for x in all_sizes) * ms
-    host_r = torch.empty(max(tot_r, 1), dtype=torch.uint8, pin_memory=True)
-    host_m = torch.empty(max(tot_m, 1), dtype=torch.uint8, pin_memory=True)
+    host_r = _pinned("results", max(tot_r, 1))
+    host_m = _pinned("matches", max(tot_m, 1))
     pr = pm = 0
     for r in range(world):
         nr, nm = all_sizes[r][0] * rs, all_sizes[r][1] * ms
@@ -158,7 +171,7 @@ def gather_results_device(matcher, n_pairs_total: int, dst: int = 0, group=None)
         pr += nr; pm += nm
     torch.cuda.synchronize(matcher.device)
     res_all = host_r[:tot_r].numpy().view(L.RESULT_DTYPE).copy()
-    m_all = host_m[:tot_m].numpy().view(L.MATCH_DTYPE)
+    m_all = host_m[:tot_m].numpy().view(L.MATCH_DTYPE)          # view of the reusable pinned buffer: valid until the next gather
     per_res, pos, base = [], 0, 0
     for r in range(world):
         nr, nm = all_sizes[r]
