@@ -213,6 +213,10 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=2)
     ap.add_argument("--cpu-budget-s", type=float, default=15.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--orb-engine", default="tensor", choices=["popc", "tensor"],
+                    help="tensor = FP8 tensor-core engine (bits as 0/1 e4m3 through tcgen05; default, fastest); "
+                         "popc = XOR+POPC kernel (the engine BASELINE.json's north_star describes). Bit-identical results; "
+                         "the other engine is timed too and reported under `engines`.")
     args = ap.parse_args()
     wl = WORKLOADS[args.workload]
     if args.impl == "reference":
@@ -255,7 +259,7 @@ def main():
     my_pairs = D.shard_pairs(all_pairs, rank, world)
     images = make_images(kind, n_images, n_desc, seed=2) if rank == 0 else None
 
-    m = eacham_b200.FeatureMatcherGpu(0.8, device=local_rank)
+    m = eacham_b200.FeatureMatcherGpu(0.8, device=local_rank, orb_engine=args.orb_engine)
     # ---- descriptors resident in HBM --------------------------------------------------------------------
     if dist is None:
         m.Upload(images)
@@ -282,6 +286,34 @@ def main():
     clocks = sampler.stop()
     total_ms = max_over_ranks(float(sum(kernel_ms)))
     value = n_pairs * args.steps / (total_ms * 1e-3)
+
+    # ---- the other ORB engine, same data, same pairs (so that both the tensor-core and the XOR+POPC numbers are in every run) ----
+    engines = None
+    if kind == "orb":
+        other = "popc" if args.orb_engine == "tensor" else "tensor"
+        m2 = eacham_b200.FeatureMatcherGpu(0.8, device=local_rank, orb_engine=other)
+        if dist is None:
+            m2.Upload(images)
+        else:
+            D.upload_and_broadcast(m2, images, src=0)
+        alt_steps = max(1, min(2, args.steps))
+        m2.MatchPairsDevice(my_pairs)
+        alt_ms = []
+        for _ in range(alt_steps):
+            m2.flush_l2(256 << 20)
+            barrier()
+            m2.MatchPairsDevice(my_pairs)
+            alt_ms.append(m2.timing()["kernel_ms"])
+        barrier()
+        alt_total = max_over_ranks(float(sum(alt_ms)))
+        m2.close()
+        popc_peak = 148 * 16.0 * peaks()["sm_max_mhz"] * 1e6
+        def eng(v):
+            return {"value": v, "unit": "pairs/s", "frac_of_popc_roofline": v * 8.0 * n_desc * n_desc / world / popc_peak}
+        engines = {args.orb_engine: dict(eng(value), steps=args.steps, default=True),
+                   other: dict(eng(n_pairs * alt_steps / (alt_total * 1e-3)), steps=alt_steps, default=False),
+                   "note": "tensor = tc_match_pairs_kernel<orb> (tcgen05 kind::f8f6f4, bits as e4m3 0/1, exact); popc = orb_match_pairs_kernel "
+                           "(XOR + carry-save POPC); identical outputs (tests/test_gpu_orb_tensor.py)"}
 
     # ---- end to end through the C ABI: host descriptors in, host results out ----------------------------
     e2e_steps = max(1, min(args.e2e_steps, args.steps))
@@ -340,11 +372,15 @@ def main():
                     "frac": achieved / peak, "traffic": traffic,
                     "peak_source": f"16.00 POPC lane-ops/clk/SM measured (profiles/r01_pipe_microbench.jsonl) x 148 SMs x sm_max_mhz "
                                    f"{pk['sm_max_mhz']:.0f} ({pk['_source']})",
-                    "work_per_pair": work_per_pair, "kernel": "orb_match_pairs_kernel",
-                    "note": "algorithmic work = 8 POPC32 per 256-bit distance, distance matrix evaluated once per pair (SURVEY.md 8(d)). "
-                            "frac > 1 is real: the kernel compresses the 8 XOR words with carry-save adders and issues 4 POPC per distance, "
-                            "so the POPC pipe is no longer the limiter; the ALU pipe (LOP3 + VIMNMX) is -- see alu_pipe.",
-                    "alu_pipe": {"achieved_tlaneops": alu_achieved / 1e12, "peak_tlaneops": alu_peak / 1e12, "frac": alu_achieved / alu_peak,
+                    "work_per_pair": work_per_pair, "kernel": "orb_match_pairs_kernel" if args.orb_engine == "popc" else "tc_match_pairs_kernel<orb>",
+                    "engine": args.orb_engine,
+                    "note": ("algorithmic work = 8 POPC32 per 256-bit distance, distance matrix evaluated once per pair (SURVEY.md 8(d)). "
+                             "frac > 1 is real: the XOR+POPC kernel compresses the 8 XOR words with carry-save adders and issues 4 POPC per "
+                             "distance, so the ALU pipe (LOP3 + VIMNMX) is its limiter -- see alu_pipe.") if args.orb_engine == "popc" else
+                            ("algorithmic work = 8 POPC32 per 256-bit distance, matrix once per pair (SURVEY.md 8(d)), kept as the yardstick; "
+                             "this engine issues no POPC at all: distances come out of tcgen05 FP8 MMAs (bits as e4m3 0/1, |a-b|^2 = hamming, exact) "
+                             "and the CUDA-core top-2 epilogue (ALU pipe) is the limiter. See `engines` for the XOR+POPC kernel on the same run."),
+                    "alu_pipe": None if args.orb_engine != "popc" else {"achieved_tlaneops": alu_achieved / 1e12, "peak_tlaneops": alu_peak / 1e12, "frac": alu_achieved / alu_peak,
                                  "ops_per_distance": alu_ops_per_distance, "peak_source": "64 lane-ops/clk/SM (LOP3 63.2 measured) x 148 x sm_max_mhz"},
                     "hbm": {"achieved_gbs": 2 * n_desc * 32 * len(my_pairs) * args.steps / (float(sum(kernel_ms)) * 1e-3) / 1e9,
                             "peak_gbs": pk["hbm_gbs"], "note": "algorithmic bytes = both images of every pair; far from the HBM bound"}}
@@ -377,7 +413,7 @@ def main():
             "value": value, "unit": "pairs/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "u8" if kind == "orb" else "f32", "data": "synthetic",
-            "config": workload_config(args, wl, n_images, n_pairs),
+            "config": dict(workload_config(args, wl, n_images, n_pairs), orb_engine=args.orb_engine) if kind == "orb" else workload_config(args, wl, n_images, n_pairs),
             "e2e": {"value": e2e_value, "unit": "pairs/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                     "steps": e2e_steps, "includes": "set_descriptors + commit (pinned staging, one H2D)" +
                     (" + NCCL arena broadcast" if world > 1 else "") + " + pair list H2D + kernel + D2H of results and matches" +
@@ -389,6 +425,7 @@ def main():
             "upload_ms": upload_ms, "arena_bytes": int(arena_bytes), "wall_s_timed_region": wall_s,
             "matches_per_step": int(res_all["count"].sum()),
             "match_api": match_api,
+            "engines": engines,
         }
         print(json.dumps(line))
     m.close()

@@ -13,6 +13,7 @@ ERR_BUFFER_TOO_SMALL, ERR_NOT_COMMITTED, ERR_TOO_LARGE, ERR_KIND_MISMATCH = -5, 
 KIND_ORB256, KIND_F32X128 = 0, 1
 NONE = 0xFFFFFFFF
 PAIR_GATED, PAIR_CONNECTED = 1, 2
+CFG_SIFT_EXACT_FP32, CFG_ORB_POPC = 1, 2
 
 
 class Config(ctypes.Structure):

@@ -279,7 +279,7 @@ int eacham_gpu_commit(eacham_gpu_handle* h) {
     h->tc_bytes = 0;
     for (size_t i = 0; i < h->images.size(); ++i) {
         const ImageHost& im = h->images[i];
-        if (im.present && im.kind == EACHAM_KIND_F32X128) {
+        if (im.present && (im.kind == EACHAM_KIND_F32X128 || !(h->cfg_flags & EACHAM_CFG_ORB_POPC))) {
             h->tc_offsets[i] = h->tc_bytes;
             h->tc_bytes += (size_t)((im.rows + 127) / 128) * eacham::tc::kBlockBytes;
         }
@@ -465,10 +465,13 @@ int prepare_tc(eacham_gpu_handle* h) {
         const ImageHost& im = h->images[i];
         table[i].offset = im.offset; table[i].tc_offset = h->tc_offsets[i];
         table[i].rows = im.present ? im.rows : 0; table[i].kind = im.present ? (uint32_t)im.kind : 0xffffffffu;
-        if (im.present && im.kind == EACHAM_KIND_F32X128 && im.rows > 0) {
+        if (im.present && im.rows > 0) {
             const uint32_t nblk = (im.rows + 127) / 128;
-            sift::sift_prep_kernel<<<nblk * 16, 256, 0, h->stream>>>(reinterpret_cast<const float*>(h->arena.p + im.offset), im.rows,
-                                                                      h->tc_arena.p + h->tc_offsets[i], nblk);
+            if (im.kind == EACHAM_KIND_F32X128)
+                sift::sift_prep_kernel<<<nblk * 16, 256, 0, h->stream>>>(reinterpret_cast<const float*>(h->arena.p + im.offset), im.rows,
+                                                                          h->tc_arena.p + h->tc_offsets[i], nblk);
+            else if (!(h->cfg_flags & EACHAM_CFG_ORB_POPC))
+                sift::orb_tc_prep_kernel<<<nblk * 16, 256, 0, h->stream>>>(h->arena.p + im.offset, im.rows, h->tc_arena.p + h->tc_offsets[i], nblk);
         }
     }
     CUDA_TRY(cudaGetLastError());
@@ -512,7 +515,9 @@ int launch_pairs(eacham_gpu_handle* h, const eacham_pair_t* pairs, size_t n_pair
                                                : std::max((size_t)1 << 20, n_pairs * (size_t)192);
     if (h->d_matches.cap < want_entries && (rc = h->d_matches.ensure(want_entries))) return rc;
 
-    if (kind == EACHAM_KIND_F32X128 && !(h->cfg_flags & 1u) && (rc = prepare_tc(h))) return rc;
+    const bool use_tc = (kind == EACHAM_KIND_F32X128 && !(h->cfg_flags & EACHAM_CFG_SIFT_EXACT_FP32)) ||
+                        (kind == EACHAM_KIND_ORB256 && !(h->cfg_flags & EACHAM_CFG_ORB_POPC));
+    if (use_tc && (rc = prepare_tc(h))) return rc;
     CUDA_TRY(cudaEventRecord(h->ev[2], h->stream));
     CUDA_TRY(cudaMemcpyAsync(h->d_pairs.p, pairs, n_pairs * sizeof(eacham_pair_t), cudaMemcpyHostToDevice, h->stream));
     CUDA_TRY(cudaEventRecord(h->ev[3], h->stream));
@@ -521,7 +526,7 @@ int launch_pairs(eacham_gpu_handle* h, const eacham_pair_t* pairs, size_t n_pair
         CUDA_TRY(cudaMemsetAsync(h->d_counter.p, 0, sizeof(uint32_t), h->stream));
         CUDA_TRY(cudaMemsetAsync(h->d_cursor.p, 0, sizeof(unsigned long long), h->stream));
         CUDA_TRY(cudaEventRecord(h->ev[4], h->stream));
-        if (kind == EACHAM_KIND_ORB256 && max_first <= orb::kMaxRowsFused && max_second <= orb::kMaxRowsFused) {
+        if (kind == EACHAM_KIND_ORB256 && !use_tc && max_first <= orb::kMaxRowsFused && max_second <= orb::kMaxRowsFused) {
             orb::PairParams p;
             p.arena = h->arena.p; p.images = h->d_images.p; p.pairs = h->d_pairs.p; p.n_pairs = (uint32_t)n_pairs;
             p.work_counter = h->d_counter.p;
@@ -536,8 +541,9 @@ int launch_pairs(eacham_gpu_handle* h, const eacham_pair_t* pairs, size_t n_pair
             orb::orb_match_pairs_kernel<<<grid, orb::kThreads, smem, h->stream>>>(p);
             CUDA_TRY(cudaGetLastError());
             h->timing.kernel_launches += 1;
-        } else if (kind == EACHAM_KIND_F32X128 && !(h->cfg_flags & 1u)) {
-            // tensor-core scorer + exact FP32 re-rank, one persistent CTA per pair
+        } else if (use_tc) {
+            // tensor-core engine, one persistent CTA per pair: SIFT = bf16 scoring + exact FP32 re-rank; ORB (default engine) = FP8 {0,1}
+            // operands, distances exact in the accumulator
             sift::PairParamsTc p;
             p.arena = h->arena.p; p.tc_arena = h->tc_arena.p; p.images = h->d_images_tc.p; p.pairs = h->d_pairs.p; p.n_pairs = (uint32_t)n_pairs;
             p.ratio = o.ratio; p.min_dir = o.min_dir; p.min_mutual = o.min_mutual; p.cross_check = o.cross_check; p.emit_all = o.emit_all;
@@ -547,8 +553,13 @@ int launch_pairs(eacham_gpu_handle* h, const eacham_pair_t* pairs, size_t n_pair
             if ((rc = h->tc_scratch.ensure(sift::tc_scratch_bytes_per_cta(p.rows_cap, p.cols_cap) * grid))) return rc;
             p.scratch = h->tc_scratch.p;
             const size_t smem = sizeof(sift::SmemTc) + 128;
-            CUDA_TRY(cudaFuncSetAttribute(sift::sift_match_pairs_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            sift::sift_match_pairs_kernel<<<grid, sift::kThreadsTc, smem, h->stream>>>(p);
+            if (kind == EACHAM_KIND_ORB256) {
+                CUDA_TRY(cudaFuncSetAttribute(sift::tc_match_pairs_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                sift::tc_match_pairs_kernel<true><<<grid, sift::kThreadsTc, smem, h->stream>>>(p);
+            } else {
+                CUDA_TRY(cudaFuncSetAttribute(sift::tc_match_pairs_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                sift::tc_match_pairs_kernel<false><<<grid, sift::kThreadsTc, smem, h->stream>>>(p);
+            }
             CUDA_TRY(cudaGetLastError());
             h->timing.kernel_launches += 1;
         } else {

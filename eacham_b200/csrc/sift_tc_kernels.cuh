@@ -10,6 +10,7 @@
 #pragma once
 #include <cstdint>
 #include <cuda_bf16.h>
+#include <cuda_fp8.h>
 #include <cuda_runtime.h>
 #include "../../include/eacham_gpu.h"
 #include "tc_common.cuh"
@@ -66,6 +67,44 @@ __global__ void __launch_bounds__(256) sift_prep_kernel(const float* __restrict_
                        q3 = __halves2bfloat162(e[6], e[7]);
         w.x = *reinterpret_cast<uint32_t*>(&q0); w.y = *reinterpret_cast<uint32_t*>(&q1);
         w.z = *reinterpret_cast<uint32_t*>(&q2); w.w = *reinterpret_cast<uint32_t*>(&q3);
+        *reinterpret_cast<uint4*>(blk + (size_t)(tc::kDataChunks + lane) * tc::kChunkStride + r * 16) = w;
+    }
+}
+
+// 256-bit ORB rows [rows][32 bytes] -> the SAME pre-tiled block geometry, one FP8 (e4m3) element per bit: 0x00 = 0.0,
+// 0x38 = 1.0. 256 elements = 256 bytes = 16 K-chunks; the augmentation chunks carry -n/2 (n = popcount of the row) split
+// into three exactly representable e4m3 pieces (16*(n>>5), (n>>1)&15, (n&1)/2) and three ones. For 0/1 vectors
+// |a-b|^2 = popcount(a xor b), so with negate-A the FP8 MMA yields D = hamming(a,b)/2 EXACTLY (all partial sums are small
+// multiples of 1/2). This is the default engine for ORB pairs; EACHAM_CFG_ORB_POPC selects the XOR+POPC kernel (orb_kernels.cuh) instead.
+__global__ void __launch_bounds__(256) orb_tc_prep_kernel(const uint8_t* __restrict__ src, uint32_t rows, uint8_t* __restrict__ dst,
+                                                          uint32_t n_blocks) {
+    const uint32_t row = blockIdx.x * 8 + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (row >= n_blocks * tc::kBlockRows) return;
+    uint8_t* blk = dst + (size_t)(row / tc::kBlockRows) * tc::kBlockBytes;
+    const uint32_t r = row % tc::kBlockRows;
+    const uint32_t byte = (row < rows) ? (uint32_t)__ldg(src + (size_t)row * 32 + lane) : 0u;
+    const uint32_t n = __reduce_add_sync(0xffffffffu, (uint32_t)__popc(byte));
+    uint2 out = make_uint2(0u, 0u);
+#pragma unroll
+    for (int b = 0; b < 4; ++b) {
+        if (byte & (1u << b)) out.x |= 0x38u << (8 * b);
+        if (byte & (16u << b)) out.y |= 0x38u << (8 * b);
+    }
+    *reinterpret_cast<uint2*>(blk + (size_t)(lane >> 1) * tc::kChunkStride + r * 16 + (lane & 1) * 8) = out;
+    if (lane < 4) {
+        uint32_t hi, mid, lo;
+        if (row < rows) {
+            hi = __nv_cvt_float_to_fp8(-16.f * (float)(n >> 5), __NV_SATFINITE, __NV_E4M3);
+            mid = __nv_cvt_float_to_fp8(-(float)((n >> 1) & 15u), __NV_SATFINITE, __NV_E4M3);
+            lo = __nv_cvt_float_to_fp8((n & 1u) ? -0.5f : 0.f, __NV_SATFINITE, __NV_E4M3);
+        } else {
+            hi = mid = lo = 0xFEu;                       // -448 each: padding rows score >= 416 > 128 = the largest real D
+        }
+        const uint32_t one = 0x38u;
+        uint4 w = make_uint4(0u, 0u, 0u, 0u);
+        if (lane == 0) { w.x = hi | (mid << 8) | (lo << 16) | (one << 24); w.y = one | (one << 8); }           // A-role
+        if (lane == 2) { w.x = one | (one << 8) | (one << 16) | (hi << 24); w.y = mid | (lo << 8); }           // B-role
         *reinterpret_cast<uint4*>(blk + (size_t)(tc::kDataChunks + lane) * tc::kChunkStride + r * 16) = w;
     }
 }
@@ -171,6 +210,15 @@ __device__ __forceinline__ uint32_t rerank_ratio(const float* __restrict__ qrow,
     return ((double)__fdiv_rn(d0, d1) < ratio) ? j0 : EACHAM_NONE;
 }
 
+// ORB engine: the composite keys already hold the exact distance (D = hamming/2 has <= 9 significant bits, so the index
+// byte displaced nothing): ratio test straight from them. (d0/2)/(d1/2) == d0/d1 in floating point, bit for bit.
+__device__ __forceinline__ uint32_t comp_ratio(long long k0, long long k1, uint32_t n_train, double ratio) {
+    const uint32_t j0 = (uint32_t)k0, j1 = (uint32_t)k1;
+    if (!(j0 < n_train && j1 < n_train)) return EACHAM_NONE;          // fewer than two neighbours: rejected
+    const float d0 = __int_as_float((int)(k0 >> 32) << 8), d1 = __int_as_float((int)(k1 >> 32) << 8);
+    return ((double)__fdiv_rn(d0, d1) < ratio) ? j0 : EACHAM_NONE;    // 0/0 -> NaN -> rejected
+}
+
 // key = (value bits & 0xFFFFFF00) | index byte, as ONE LOP3 ((a & b) | c, LUT 0xEA)
 __device__ __forceinline__ int32_t make_key(uint32_t v, uint32_t mask, uint32_t idx) {
     uint32_t r;
@@ -213,7 +261,8 @@ __device__ __forceinline__ void epi_tile(uint32_t acc_taddr, int cp, int q, int 
     }
 }
 
-__global__ void __launch_bounds__(kThreadsTc, 1) sift_match_pairs_kernel(const PairParamsTc p) {
+template <bool kOrb>
+__global__ void __launch_bounds__(kThreadsTc, 1) tc_match_pairs_kernel(const PairParamsTc p) {
     extern __shared__ __align__(128) uint8_t smem_raw[];
     SmemTc& S = *reinterpret_cast<SmemTc*>(smem_raw);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -262,7 +311,7 @@ __global__ void __launch_bounds__(kThreadsTc, 1) sift_match_pairs_kernel(const P
         // ===================================== MMA issuer =====================================
         if (lane == 0) {
             const uint64_t dbase = tc::make_smem_desc_base(tc::kLBO, tc::kSBO);
-            const uint32_t idesc = tc::make_idesc_bf16_f32(128, 128, true);
+            const uint32_t idesc = kOrb ? tc::make_idesc_e4m3_f32(128, 128, true) : tc::make_idesc_bf16_f32(128, 128, true);
             uint32_t b_it = 0, a_it = 0, acc_it = 0;
             for (uint32_t pi = blockIdx.x; pi < p.n_pairs; pi += gridDim.x) {
                 const eacham_pair_t pr = p.pairs[pi];
@@ -283,8 +332,12 @@ __global__ void __launch_bounds__(kThreadsTc, 1) sift_match_pairs_kernel(const P
                             const uint32_t d = tmem + as * 256 + h * 128;
 #pragma unroll
                             for (int ks = 0; ks < tc::kKSteps; ++ks)
-                                tc::mma_bf16(d, tc::smem_desc(dbase, a_addr + ks * 2 * tc::kChunkStride),
-                                             tc::smem_desc(dbase, b_addr + ks * 2 * tc::kChunkStride), idesc, ks > 0);
+                            {
+                                const uint64_t da = tc::smem_desc(dbase, a_addr + ks * 2 * tc::kChunkStride);
+                                const uint64_t db = tc::smem_desc(dbase, b_addr + ks * 2 * tc::kChunkStride);
+                                if (kOrb) tc::mma_f8(d, da, db, idesc, ks > 0);
+                                else tc::mma_bf16(d, da, db, idesc, ks > 0);
+                            }
                         }
                         tc::mma_commit(&S.b_empty[st]);      // B stage reusable once these MMAs have read it
                         tc::mma_commit(&S.acc_full[as]);     // accumulators ready for the epilogue
@@ -379,10 +432,16 @@ __global__ void __launch_bounds__(kThreadsTc, 1) sift_match_pairs_kernel(const P
                             const long long b1 = ((long long)(o.y >> 8) << 32) | (long long)((uint32_t)o.w * 128 + c * kColsPerWarp + (o.y & 0xFF));
                             comp_merge(b0, b1, a0, a1);
                         }
-                        S.rowcand[h * 128 + q * 32 + lane] = make_uint2((uint32_t)a0, (uint32_t)a1);
+                        if (kOrb) {                                   // exact distances are in the keys: no re-rank
+                            const uint32_t row = ab * kABlockRows + h * 128 + q * 32 + lane;
+                            if (row < N) m12[row] = comp_ratio(a0, a1, M, p.ratio);
+                        } else {
+                            S.rowcand[h * 128 + q * 32 + lane] = make_uint2((uint32_t)a0, (uint32_t)a1);
+                        }
                     }
                 }
                 epi_bar();
+                if (!kOrb)
                 for (int r = 0; r < kABlockRows / kEpiWarps; ++r) {
                     const uint32_t lr = e * (kABlockRows / kEpiWarps) + r, row = ab * kABlockRows + lr;
                     if (row < N) {
@@ -396,10 +455,14 @@ __global__ void __launch_bounds__(kThreadsTc, 1) sift_match_pairs_kernel(const P
 
             // ---- columns: re-rank, ratio -> m21 ----
             __threadfence_block();
-            for (uint32_t j = e; j < M; j += kEpiWarps) {
-                const long long k0 = colstate[2 * j], k1 = colstate[2 * j + 1];
-                const uint32_t mm = rerank_ratio(Bf + (size_t)j * 128, Af, (uint32_t)k0, (uint32_t)k1, N, p.ratio, lane);
-                if (lane == 0) m21[j] = mm;
+            if (kOrb) {
+                for (uint32_t j = et; j < M; j += kEpiThreads) m21[j] = comp_ratio(colstate[2 * j], colstate[2 * j + 1], N, p.ratio);
+            } else {
+                for (uint32_t j = e; j < M; j += kEpiWarps) {
+                    const long long k0 = colstate[2 * j], k1 = colstate[2 * j + 1];
+                    const uint32_t mm = rerank_ratio(Bf + (size_t)j * 128, Af, (uint32_t)k0, (uint32_t)k1, N, p.ratio, lane);
+                    if (lane == 0) m21[j] = mm;
+                }
             }
             __threadfence_block();
             epi_bar();

@@ -79,6 +79,17 @@ __device__ __forceinline__ void mma_bf16(uint32_t tmem_d, uint64_t desc_a, uint6
         "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
         ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate) : "memory");
 }
+// FP8 (e4m3 x e4m3 -> f32) variant: one K=32 step (32 bytes per row, i.e. the same two 16-byte K-chunks as a bf16 K=16 step)
+__host__ __device__ constexpr uint32_t make_idesc_e4m3_f32(uint32_t m, uint32_t n, bool negate_a) {
+    return (1u << 4) | ((negate_a ? 1u : 0u) << 13) | ((n >> 3) << 17) | ((m >> 4) << 24);      // A/B format 0 = E4M3
+}
+__device__ __forceinline__ void mma_f8(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f8f6f4 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate) : "memory");
+}
 // all previously issued MMAs of this thread arrive on the mbarrier when they complete (implies fence::before_thread_sync)
 __device__ __forceinline__ void mma_commit(uint64_t* bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");

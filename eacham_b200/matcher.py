@@ -62,12 +62,17 @@ class FeatureMatcherGpu:
     MatchType = dict
 
     def __init__(self, inliersRatio: float = 0.8, *, ratio: float = 0.8, device: int = 0, min_dir: int = 30,
-                 min_mutual: int = 30, cross_check: bool = True, match_buffer_entries: int = 0):
+                 min_mutual: int = 30, cross_check: bool = True, match_buffer_entries: int = 0,
+                 orb_engine: str = "tensor", sift_exact_fp32: bool = False):
         self.inliersRatio = float(inliersRatio)
         self.ratio = float(ratio)
         self.min_dir, self.min_mutual, self.cross_check = int(min_dir), int(min_mutual), bool(cross_check)
         self._lib = L.load()
-        cfg = L.Config(device=device, max_images=0, match_buffer_entries=match_buffer_entries, flags=0)
+        if orb_engine not in ("popc", "tensor"):
+            raise ValueError("orb_engine must be 'tensor' (FP8 tensor-core engine, default) or 'popc' (XOR+POPC kernel)")
+        flags = (L.CFG_SIFT_EXACT_FP32 if sift_exact_fp32 else 0) | (L.CFG_ORB_POPC if orb_engine == "popc" else 0)
+        self.orb_engine = orb_engine
+        cfg = L.Config(device=device, max_images=0, match_buffer_entries=match_buffer_entries, flags=flags)
         h = ctypes.c_void_p()
         L.check(self._lib.eacham_gpu_create(ctypes.byref(cfg), ctypes.byref(h)))
         self._h = h

@@ -60,13 +60,14 @@ typedef enum eacham_kind {
 
 typedef struct eacham_gpu_handle eacham_gpu_handle;
 
-#define EACHAM_CFG_SIFT_EXACT_FP32 1u
+#define EACHAM_CFG_SIFT_EXACT_FP32 1u  /* SIFT pairs on the all-FP32 kernels (no tensor cores)                          */
+#define EACHAM_CFG_ORB_POPC 2u         /* ORB pairs on the XOR+POPC kernel instead of the default tensor-core engine (bits as FP8 0/1, exact) */
 
 typedef struct eacham_gpu_config {
     int32_t device;               /* CUDA device ordinal                                                     */
     uint32_t max_images;          /* 0 = grow on demand                                                      */
     uint64_t match_buffer_entries;/* device-side capacity for compacted matches; 0 = sized per call          */
-    uint32_t flags;               /* bit 0: EACHAM_CFG_SIFT_EXACT_FP32 -- SIFT pairs on the all-FP32 kernels (no tensor cores) */
+    uint32_t flags;               /* EACHAM_CFG_* bits                                                        */
 } eacham_gpu_config;
 
 /* {queryIdx -> trainIdx}: one entry of the reference's std::unordered_map<unsigned, unsigned>. */

@@ -12,6 +12,15 @@ pytestmark = pytest.mark.gpu
 NONE = 0xFFFFFFFF
 
 
+@pytest.fixture(scope="module", params=["tensor", "popc"])
+def matcher(request):
+    """Every test below runs on both ORB engines: the tcgen05 FP8 engine (default) and the XOR+POPC kernel."""
+    import eacham_b200
+    m = eacham_b200.FeatureMatcherGpu(0.8, orb_engine=request.param)
+    yield m
+    m.close()
+
+
 def _map_arr(m, n):
     a = np.full(n, NONE, np.uint32)
     for k, v in m.items():
@@ -95,12 +104,12 @@ def test_options_ratio_and_gates(matcher):
     a, b = cases.planted_pair(rng, 600, 640, 50, d_good=60)
     import eacham_b200
     for ratio, min_dir, min_mutual in ((0.8, 30, 30), (0.7, 10, 5), (0.95, 0, 0), (0.5, 1, 0)):
-        with eacham_b200.FeatureMatcherGpu(0.8, ratio=ratio, min_dir=min_dir, min_mutual=min_mutual) as m:
+        with eacham_b200.FeatureMatcherGpu(0.8, ratio=ratio, min_dir=min_dir, min_mutual=min_mutual, orb_engine=matcher.orb_engine) as m:
             m.Upload([a, b])
             pm = m.MatchPairs([(0, 1)], emit_all=True)[0]
             _assert_pair_equal(pm, O.c_match_pair(a, b, ratio, min_dir, min_mutual), f"ratio {ratio}")
             assert m.Match(a, b) == O.c_match(a, b, ratio)
-    with eacham_b200.FeatureMatcherGpu(0.8, cross_check=False) as m:      # first -> second direction only
+    with eacham_b200.FeatureMatcherGpu(0.8, cross_check=False, orb_engine=matcher.orb_engine) as m:      # first -> second direction only
         m.Upload([a, b])
         pm = m.MatchPairs([(0, 1)], emit_all=True)[0]
         assert pm.best12() == O.c_match(a, b)
@@ -137,7 +146,7 @@ def test_concurrent_match_calls_on_one_handle(matcher):
 def test_error_codes(matcher):
     from eacham_b200 import _lib as L
     import eacham_b200
-    with eacham_b200.FeatureMatcherGpu(0.8) as m:
+    with eacham_b200.FeatureMatcherGpu(0.8, orb_engine=matcher.orb_engine) as m:
         with pytest.raises(L.EachamGpuError) as e:
             m.MatchPairs([(0, 1)])
         assert e.value.code == L.ERR_NOT_COMMITTED
