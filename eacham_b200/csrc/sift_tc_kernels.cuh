@@ -99,7 +99,9 @@ __global__ void __launch_bounds__(256) orb_tc_prep_kernel(const uint8_t* __restr
             mid = __nv_cvt_float_to_fp8(-(float)((n >> 1) & 15u), __NV_SATFINITE, __NV_E4M3);
             lo = __nv_cvt_float_to_fp8((n & 1u) ? -0.5f : 0.f, __NV_SATFINITE, __NV_E4M3);
         } else {
-            hi = mid = lo = 0xFEu;                       // -448 each: padding rows score >= 416 > 128 = the largest real D
+            hi = __nv_cvt_float_to_fp8(-256.f, __NV_SATFINITE, __NV_E4M3);     // padding rows: n/2 = 300, so they score
+            mid = __nv_cvt_float_to_fp8(-32.f, __NV_SATFINITE, __NV_E4M3);     // D >= 300 > 128 (largest real D) and pad x pad
+            lo = __nv_cvt_float_to_fp8(-12.f, __NV_SATFINITE, __NV_E4M3);      // = 600 still fits the packed 16-bit row keys
         }
         const uint32_t one = 0x38u;
         uint4 w = make_uint4(0u, 0u, 0u, 0u);
@@ -210,13 +212,55 @@ __device__ __forceinline__ uint32_t rerank_ratio(const float* __restrict__ qrow,
     return ((double)__fdiv_rn(d0, d1) < ratio) ? j0 : EACHAM_NONE;
 }
 
-// ORB engine: the composite keys already hold the exact distance (D = hamming/2 has <= 9 significant bits, so the index
-// byte displaced nothing): ratio test straight from them. (d0/2)/(d1/2) == d0/d1 in floating point, bit for bit.
+// ORB engine: composites carry the exact Hamming distance (an integer) in their high word: ratio test straight from them.
 __device__ __forceinline__ uint32_t comp_ratio(long long k0, long long k1, uint32_t n_train, double ratio) {
     const uint32_t j0 = (uint32_t)k0, j1 = (uint32_t)k1;
     if (!(j0 < n_train && j1 < n_train)) return EACHAM_NONE;          // fewer than two neighbours: rejected
-    const float d0 = __int_as_float((int)(k0 >> 32) << 8), d1 = __int_as_float((int)(k1 >> 32) << 8);
+    const float d0 = (float)(uint32_t)(k0 >> 32), d1 = (float)(uint32_t)(k1 >> 32);
     return ((double)__fdiv_rn(d0, d1) < ratio) ? j0 : EACHAM_NONE;    // 0/0 -> NaN -> rejected
+}
+
+// ORB epilogue. TMEM holds D = hamming/2 exactly (real pairs <= 128, padding 300..600). Keys are built on the FMA pipe with a
+// magic-number FFMA: the low mantissa bits of fma(D, 2^s, 2^23 + idx) are (2D << (s-1)) | idx.
+//   rows:    16-bit key (2D << 5) | column-in-part (5 bits); the keys of the thread's two rows are packed into one word
+//            (PRMT) and the running top-2 of BOTH rows is updated with three VIMNMX.U16x2;
+//   columns: 32-bit key (2D << 8) | row-in-block (8 bits) under the constant exponent bits, then min/max + two REDUX.MIN as
+//            in the float version.
+// 9 ALU-pipe instructions per column (two scores) instead of 15.
+template <int NH>
+__device__ __forceinline__ void epi_tile_orb(uint32_t acc_taddr, int cp, int q, int lane, uint32_t& m0x2, uint32_t& m1x2,
+                                             uint2* __restrict__ slot_q) {
+    const float cr0 = 8388608.f + (float)(q * 32 + lane), cr1 = 8388608.f + (float)(128 + q * 32 + lane);
+#pragma unroll
+    for (int ch = 0; ch < kColsPerWarp / 16; ++ch) {
+        uint32_t v0[16], v1[16];
+        tc::tmem_ld16(acc_taddr + cp * kColsPerWarp + ch * 16, v0);
+        if (NH == 2) tc::tmem_ld16(acc_taddr + 128 + cp * kColsPerWarp + ch * 16, v1);
+        tc::tmem_ld_wait();
+#pragma unroll
+        for (int k = 0; k < 16; ++k) {
+            const int idx = ch * 16 + k;
+            const float cidx = 8388608.f + (float)idx;
+            const float f0 = __uint_as_float(v0[k]);
+            const uint32_t x0 = __float_as_uint(fmaf(f0, 64.f, cidx));
+            uint32_t x1 = 0xFFFFFFFFu;
+            uint32_t lo = __float_as_uint(fmaf(f0, 512.f, cr0)), hi = (uint32_t)kEmptyKeyTc;
+            if (NH == 2) {
+                const float f1 = __uint_as_float(v1[k]);
+                x1 = __float_as_uint(fmaf(f1, 64.f, cidx));
+                const uint32_t kc1 = __float_as_uint(fmaf(f1, 512.f, cr1));
+                hi = max(lo, kc1);
+                lo = min(lo, kc1);
+            }
+            const uint32_t kr = __byte_perm(x0, x1, 0x5410);          // low halves: row h=0 | row h=1 << 16
+            m1x2 = __vminu2(m1x2, __vmaxu2(m0x2, kr));
+            m0x2 = __vminu2(m0x2, kr);
+            const uint32_t g0 = __reduce_min_sync(0xffffffffu, lo);
+            const uint32_t x = (lo == g0) ? hi : lo;
+            const uint32_t g1 = __reduce_min_sync(0xffffffffu, x);
+            slot_q[cp * kColsPerWarp + idx] = make_uint2(g0, g1);
+        }
+    }
 }
 
 // key = (value bits & 0xFFFFFF00) | index byte, as ONE LOP3 ((a & b) | c, LUT 0xEA)
@@ -376,19 +420,28 @@ __global__ void __launch_bounds__(kThreadsTc, 1) tc_match_pairs_kernel(const Pai
             for (uint32_t ab = 0; ab * 2 < na128; ++ab) {
                 const uint32_t nh = min(2u, na128 - ab * 2);
                 int32_t m0[2] = {kEmptyKeyTc, kEmptyKeyTc}, m1[2] = {kEmptyKeyTc, kEmptyKeyTc};
+                uint32_t m0x2 = 0xFFFFFFFFu, m1x2 = 0xFFFFFFFFu;           // ORB: packed 16-bit row keys of both rows
                 uint32_t t0[2] = {0xFFFFu, 0xFFFFu}, t1[2] = {0xFFFFu, 0xFFFFu};
                 for (uint32_t bt = 0; bt < nbt; ++bt, ++acc_it) {
                     const uint32_t as = acc_it % kAccStages;
                     // column state of this tile: issue the (L2) load early, consumed after the barrier
                     long long c0 = 0, c1 = 0;
                     if (et < 128) { c0 = colstate[2 * (bt * 128 + et)]; c1 = colstate[2 * (bt * 128 + et) + 1]; }
+                    if (kOrb) { m0[0] = (int32_t)(m0x2 & 0xFFFFu); m0[1] = (int32_t)(m0x2 >> 16); m1[0] = (int32_t)(m1x2 & 0xFFFFu); m1[1] = (int32_t)(m1x2 >> 16); }
                     const int32_t o00 = m0[0], o10 = m1[0], o01 = m0[1], o11 = m1[1];
                     tc::mbar_wait(&S.acc_full[as], (acc_it / kAccStages) & 1);
                     tc::tc_fence_after();
                     const uint32_t taddr = tmem + as * 256 + ((uint32_t)(q * 32) << 16);
                     uint2* slot_q = S.slots[bt & 1][q];
-                    if (nh == 2) epi_tile<2>(taddr, cp, q, lane, m0, m1, slot_q);
-                    else epi_tile<1>(taddr, cp, q, lane, m0, m1, slot_q);
+                    if (kOrb) {
+                        if (nh == 2) epi_tile_orb<2>(taddr, cp, q, lane, m0x2, m1x2, slot_q);
+                        else epi_tile_orb<1>(taddr, cp, q, lane, m0x2, m1x2, slot_q);
+                        m0[0] = (int32_t)(m0x2 & 0xFFFFu); m0[1] = (int32_t)(m0x2 >> 16);
+                        m1[0] = (int32_t)(m1x2 & 0xFFFFu); m1[1] = (int32_t)(m1x2 >> 16);
+                    } else {
+                        if (nh == 2) epi_tile<2>(taddr, cp, q, lane, m0, m1, slot_q);
+                        else epi_tile<1>(taddr, cp, q, lane, m0, m1, slot_q);
+                    }
                     tc::tc_fence_before();
                     __syncwarp();
                     if (lane == 0) tc::mbar_arrive(&S.acc_empty[as]);       // TMEM stage free for the next MMA
@@ -405,8 +458,11 @@ __global__ void __launch_bounds__(kThreadsTc, 1) tc_match_pairs_kernel(const Pai
 #pragma unroll
                         for (int qq = 0; qq < 4; ++qq) {
                             const uint2 s = S.slots[bt & 1][qq][et];
-                            const long long k0 = ((long long)((int32_t)s.x >> 8) << 32) | (long long)(ab * kABlockRows + (s.x & 0xFFu));
-                            const long long k1 = ((long long)((int32_t)s.y >> 8) << 32) | (long long)(ab * kABlockRows + (s.y & 0xFFu));
+                            // value part: float path = top 24 bits of D; ORB path = the integer 2D = hamming (below the exponent bits)
+                            const long long v0 = kOrb ? (long long)((s.x >> 8) & 0x7FFFu) : (long long)((int32_t)s.x >> 8);
+                            const long long v1 = kOrb ? (long long)((s.y >> 8) & 0x7FFFu) : (long long)((int32_t)s.y >> 8);
+                            const long long k0 = (v0 << 32) | (long long)(ab * kABlockRows + (s.x & 0xFFu));
+                            const long long k1 = (v1 << 32) | (long long)(ab * kABlockRows + (s.y & 0xFFu));
                             comp_merge(k0, k1, g0, g1);
                         }
                         comp_merge(c0, c1, g0, g1);
@@ -423,13 +479,17 @@ __global__ void __launch_bounds__(kThreadsTc, 1) tc_match_pairs_kernel(const Pai
                 if (cp == 0) {
 #pragma unroll
                     for (int h = 0; h < 2; ++h) {
-                        long long a0 = ((long long)(m0[h] >> 8) << 32) | (long long)(t0[h] * 128 + (m0[h] & 0xFF));
-                        long long a1 = ((long long)(m1[h] >> 8) << 32) | (long long)(t1[h] * 128 + (m1[h] & 0xFF));
+                        // composite = (value << 32) | full column. float path: key = value bits | index byte (8 index bits);
+                        // ORB path: key = (hamming << 5) | column-in-part (5 index bits)
+                        constexpr int kIdxBits = kOrb ? 5 : 8;
+                        constexpr int kIdxMask = (1 << kIdxBits) - 1;
+                        long long a0 = ((long long)(m0[h] >> kIdxBits) << 32) | (long long)(t0[h] * 128 + (m0[h] & kIdxMask));
+                        long long a1 = ((long long)(m1[h] >> kIdxBits) << 32) | (long long)(t1[h] * 128 + (m1[h] & kIdxMask));
 #pragma unroll
                         for (int c = 1; c < kColParts; ++c) {
                             const int4 o = S.rowkeys[c - 1][h * 128 + q * 32 + lane];
-                            const long long b0 = ((long long)(o.x >> 8) << 32) | (long long)((uint32_t)o.z * 128 + c * kColsPerWarp + (o.x & 0xFF));
-                            const long long b1 = ((long long)(o.y >> 8) << 32) | (long long)((uint32_t)o.w * 128 + c * kColsPerWarp + (o.y & 0xFF));
+                            const long long b0 = ((long long)(o.x >> kIdxBits) << 32) | (long long)((uint32_t)o.z * 128 + c * kColsPerWarp + (o.x & kIdxMask));
+                            const long long b1 = ((long long)(o.y >> kIdxBits) << 32) | (long long)((uint32_t)o.w * 128 + c * kColsPerWarp + (o.y & kIdxMask));
                             comp_merge(b0, b1, a0, a1);
                         }
                         if (kOrb) {                                   // exact distances are in the keys: no re-rank
