@@ -12,8 +12,10 @@ collective, after ONE NCCL broadcast of the descriptor arena.
 value  = pairs / s with descriptors resident in HBM (CUDA events around the matching kernel on the library's stream).
 e2e    = the same through the C-ABI calls a user makes, host buffers in, host buffers out (upload + broadcast +
          match + D2H of results inside the timed region).
-roofline: the ORB kernel is bound by the POPC pipe (16 lane-ops/clk/SM measured: profiles/r01_pipe_microbench.jsonl),
-         not HBM: achieved = 8*N*M POPC32 per pair * pairs / kernel time.
+roofline: the yardstick is SURVEY.md 8(d)'s POPC roofline (8 POPC32 per 256-bit distance, matrix once per pair, POPC pipe
+         = 16 lane-ops/clk/SM measured: profiles/r01_pipe_microbench.jsonl): achieved = 8*N*M * pairs / kernel time.
+         Two ORB engines produce identical bytes and are BOTH timed in every run (`engines`): the default tcgen05 FP8 engine
+         (bits as e4m3 0/1: |a-b|^2 = hamming, exact) and the XOR+POPC kernel north_star describes.
 """
 from __future__ import annotations
 
@@ -364,7 +366,9 @@ def main():
             peak = sm_count * popc_per_clk * pk["sm_max_mhz"] * 1e6     # lane-ops/s at max clock
             achieved = work_per_pair * (len(my_pairs) * args.steps) / (float(sum(kernel_ms)) * 1e-3)
             traffic_path = os.path.join(ROOT, "profiles", "traffic.json")
-            traffic = json.load(open(traffic_path)).get(args.workload) if os.path.exists(traffic_path) else None
+            tkey = args.workload if args.orb_engine == "tensor" else args.workload + "_popc"
+            traffic = json.load(open(traffic_path)).get(tkey) if os.path.exists(traffic_path) else None
+            fp8_flops = 2.0 * 256 * n_desc * n_desc * (len(my_pairs) * args.steps) / (float(sum(kernel_ms)) * 1e-3)
             alu_ops_per_distance = 22.0        # 16 LOP3 + 6 VIMNMX issued on the ALU pipe per distance (SASS count)
             alu_peak = sm_count * 64.0 * pk["sm_max_mhz"] * 1e6
             alu_achieved = alu_ops_per_distance * n_desc * n_desc * (len(my_pairs) * args.steps) / (float(sum(kernel_ms)) * 1e-3)
@@ -380,6 +384,12 @@ def main():
                             ("algorithmic work = 8 POPC32 per 256-bit distance, matrix once per pair (SURVEY.md 8(d)), kept as the yardstick; "
                              "this engine issues no POPC at all: distances come out of tcgen05 FP8 MMAs (bits as e4m3 0/1, |a-b|^2 = hamming, exact) "
                              "and the CUDA-core top-2 epilogue (ALU pipe) is the limiter. See `engines` for the XOR+POPC kernel on the same run."),
+                    "tensor_pipe": None if args.orb_engine != "tensor" else {
+                        "achieved_tflops_fp8": fp8_flops / 1e12, "peak_tflops_fp8": 2 * pk["bf16_tflops"],
+                        "frac": fp8_flops / (2 * pk["bf16_tflops"] * 1e12),
+                        "note": "algorithmic 2*256*N*M FLOP per pair through kind::f8f6f4 MMAs vs 2 x the measured bf16 burst peak (no measured FP8 "
+                                "peak on file); ncu: tensor pipe 31%, ALU pipe 74%, issue 68% (profiles/r01d_ncu_orb_tensor_engine_summary.json) -- "
+                                "the top-2 epilogue on the CUDA cores, not the tensor core, bounds this kernel"},
                     "alu_pipe": None if args.orb_engine != "popc" else {"achieved_tlaneops": alu_achieved / 1e12, "peak_tlaneops": alu_peak / 1e12, "frac": alu_achieved / alu_peak,
                                  "ops_per_distance": alu_ops_per_distance, "peak_source": "64 lane-ops/clk/SM (LOP3 63.2 measured) x 148 x sm_max_mhz"},
                     "hbm": {"achieved_gbs": 2 * n_desc * 32 * len(my_pairs) * args.steps / (float(sum(kernel_ms)) * 1e-3) / 1e9,
