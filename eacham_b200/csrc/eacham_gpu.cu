@@ -19,7 +19,7 @@
 #include "../../include/eacham_gpu.h"
 #include "l2_kernels.cuh"
 #include "orb_kernels.cuh"
-#include "sift_tc_kernels.cuh"
+#include "tc_match_kernels.cuh"
 
 namespace {
 
@@ -93,7 +93,7 @@ struct eacham_gpu_handle {
     uint32_t max_rows[2] = {0, 0};
     // SIFT tensor-core path: pre-tiled bf16 copy of every F32X128 image, built lazily after commit (+ broadcast)
     DevBuf<uint8_t> tc_arena;
-    DevBuf<eacham::sift::ImageDescTc> d_images_tc;
+    DevBuf<eacham::tcm::ImageDescTc> d_images_tc;
     std::vector<size_t> tc_offsets;
     size_t tc_bytes = 0;
     bool tc_dirty = true;
@@ -460,7 +460,7 @@ int prepare_tc(eacham_gpu_handle* h) {
     int rc;
     if ((rc = h->tc_arena.ensure(std::max(h->tc_bytes, (size_t)tc::kBlockBytes)))) return rc;
     if ((rc = h->d_images_tc.ensure(std::max(h->images.size(), (size_t)1)))) return rc;
-    std::vector<sift::ImageDescTc> table(h->images.size());
+    std::vector<tcm::ImageDescTc> table(h->images.size());
     for (size_t i = 0; i < h->images.size(); ++i) {
         const ImageHost& im = h->images[i];
         table[i].offset = im.offset; table[i].tc_offset = h->tc_offsets[i];
@@ -468,10 +468,10 @@ int prepare_tc(eacham_gpu_handle* h) {
         if (im.present && im.rows > 0) {
             const uint32_t nblk = (im.rows + 127) / 128;
             if (im.kind == EACHAM_KIND_F32X128)
-                sift::sift_prep_kernel<<<nblk * 16, 256, 0, h->stream>>>(reinterpret_cast<const float*>(h->arena.p + im.offset), im.rows,
+                tcm::sift_prep_kernel<<<nblk * 16, 256, 0, h->stream>>>(reinterpret_cast<const float*>(h->arena.p + im.offset), im.rows,
                                                                           h->tc_arena.p + h->tc_offsets[i], nblk);
             else if (!(h->cfg_flags & EACHAM_CFG_ORB_POPC))
-                sift::orb_tc_prep_kernel<<<nblk * 16, 256, 0, h->stream>>>(h->arena.p + im.offset, im.rows, h->tc_arena.p + h->tc_offsets[i], nblk);
+                tcm::orb_tc_prep_kernel<<<nblk * 16, 256, 0, h->stream>>>(h->arena.p + im.offset, im.rows, h->tc_arena.p + h->tc_offsets[i], nblk);
         }
     }
     CUDA_TRY(cudaGetLastError());
@@ -544,21 +544,21 @@ int launch_pairs(eacham_gpu_handle* h, const eacham_pair_t* pairs, size_t n_pair
         } else if (use_tc) {
             // tensor-core engine, one persistent CTA per pair: SIFT = bf16 scoring + exact FP32 re-rank; ORB (default engine) = FP8 {0,1}
             // operands, distances exact in the accumulator
-            sift::PairParamsTc p;
+            tcm::PairParamsTc p;
             p.arena = h->arena.p; p.tc_arena = h->tc_arena.p; p.images = h->d_images_tc.p; p.pairs = h->d_pairs.p; p.n_pairs = (uint32_t)n_pairs;
             p.ratio = o.ratio; p.min_dir = o.min_dir; p.min_mutual = o.min_mutual; p.cross_check = o.cross_check; p.emit_all = o.emit_all;
             p.results = h->d_results.p; p.matches = h->d_matches.p; p.matches_cap = h->d_matches.cap; p.cursor = h->d_cursor.p;
             p.rows_cap = (uint32_t)align_up(std::max(max_first, 1u), 128); p.cols_cap = (uint32_t)align_up(std::max(max_second, 1u), 128);
             const unsigned grid = (unsigned)std::min<size_t>(n_pairs, (size_t)h->sm_count);
-            if ((rc = h->tc_scratch.ensure(sift::tc_scratch_bytes_per_cta(p.rows_cap, p.cols_cap) * grid))) return rc;
+            if ((rc = h->tc_scratch.ensure(tcm::tc_scratch_bytes_per_cta(p.rows_cap, p.cols_cap) * grid))) return rc;
             p.scratch = h->tc_scratch.p;
-            const size_t smem = sizeof(sift::SmemTc) + 128;
+            const size_t smem = sizeof(tcm::SmemTc) + 128;
             if (kind == EACHAM_KIND_ORB256) {
-                CUDA_TRY(cudaFuncSetAttribute(sift::tc_match_pairs_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-                sift::tc_match_pairs_kernel<true><<<grid, sift::kThreadsTc, smem, h->stream>>>(p);
+                CUDA_TRY(cudaFuncSetAttribute(tcm::tc_match_pairs_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                tcm::tc_match_pairs_kernel<true><<<grid, tcm::kThreadsTc, smem, h->stream>>>(p);
             } else {
-                CUDA_TRY(cudaFuncSetAttribute(sift::tc_match_pairs_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-                sift::tc_match_pairs_kernel<false><<<grid, sift::kThreadsTc, smem, h->stream>>>(p);
+                CUDA_TRY(cudaFuncSetAttribute(tcm::tc_match_pairs_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                tcm::tc_match_pairs_kernel<false><<<grid, tcm::kThreadsTc, smem, h->stream>>>(p);
             }
             CUDA_TRY(cudaGetLastError());
             h->timing.kernel_launches += 1;

@@ -1,4 +1,5 @@
-// sift_tc_kernels.cuh -- 128-d float (SIFT) matching on the 5th-gen tensor cores (tcgen05) of sm_100a.
+// tc_match_kernels.cuh -- the tensor-core matching engine (tcgen05 / TMEM, sm_100a) for both descriptor kinds:
+// 128-d float SIFT (bf16 scoring + exact FP32 re-rank) and 256-bit ORB (bits as FP8 0/1, exact).
 //
 // Replaces, for N x 128 CV_32F descriptors, per unordered image pair:
 //   knnMatch(k=2) both directions   /root/reference/modules/base/features/FeatureMatcherFlann.cpp:17  (exact NORM_L2 semantics)
@@ -16,7 +17,7 @@
 #include "tc_common.cuh"
 
 namespace eacham {
-namespace sift {
+namespace tcm {
 
 // x = hi + mid + lo exactly (24-bit significand -> 3 x 8 bits)
 __device__ __forceinline__ void split3(float x, __nv_bfloat16& hi, __nv_bfloat16& mid, __nv_bfloat16& lo) {
@@ -591,5 +592,5 @@ __global__ void __launch_bounds__(kThreadsTc, 1) tc_match_pairs_kernel(const Pai
     if (warp == 1) tc::tmem_dealloc(tmem, 512);
 }
 
-}  // namespace sift
+}  // namespace tcm
 }  // namespace eacham

@@ -41,11 +41,14 @@ public:
 
 public:
     // inliersRatio is stored and, like the reference (FeatureMatcherFlann.cpp:23 hard-codes 0.8), not used.
-    explicit FeatureMatcherGpu(const float inliersRatio, const int device = 0)
+    // flags: EACHAM_CFG_* bits (0 = defaults: tensor-core engine for ORB and SIFT; EACHAM_CFG_ORB_POPC selects the
+    // XOR+POPC kernel for ORB pairs, EACHAM_CFG_SIFT_EXACT_FP32 the all-FP32 SIFT kernels). Results do not depend on it.
+    explicit FeatureMatcherGpu(const float inliersRatio, const int device = 0, const unsigned flags = 0)
         : inliersRatio{inliersRatio}
     {
         eacham_gpu_config cfg{};
         cfg.device = device;
+        cfg.flags = flags;
         Check(eacham_gpu_create(&cfg, &handle));
         eacham_gpu_default_opts(&opts);
     }

@@ -5,7 +5,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <vector>
-#include "../eacham_b200/csrc/sift_tc_kernels.cuh"
+#include "../eacham_b200/csrc/tc_match_kernels.cuh"
 
 using namespace eacham;
 
@@ -71,8 +71,8 @@ int main() {
         cudaMemcpy(da, a.data(), a.size() * 4, cudaMemcpyHostToDevice);
         cudaMemcpy(db, b.data(), b.size() * 4, cudaMemcpyHostToDevice);
         const int rows_a = 120, rows_b = 128;      // 8 padding rows in A
-        sift::sift_prep_kernel<<<16, 256>>>(da, rows_a, ta, 1);
-        sift::sift_prep_kernel<<<16, 256>>>(db, rows_b, tb, 1);
+        tcm::sift_prep_kernel<<<16, 256>>>(da, rows_a, ta, 1);
+        tcm::sift_prep_kernel<<<16, 256>>>(db, rows_b, tb, 1);
         const size_t smem = 2 * tc::kAOperandBytes + 64;
         cudaFuncSetAttribute(tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         tile_kernel<<<1, 128, smem>>>(ta, tb, dout, 1);
