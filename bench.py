@@ -422,7 +422,9 @@ def main():
             "metric": "image pairs matched/sec (exhaustive, 4k ORB)" if args.workload == "orb4k" else f"image pairs matched/sec ({args.workload})",
             "value": value, "unit": "pairs/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "u8" if kind == "orb" else "f32", "data": "synthetic",
+            "dtype": ("u8 (XOR+POPC)" if args.orb_engine == "popc" else "u8 bits as fp8 e4m3 {0,1} -> f32 accumulate (exact integers)") if kind == "orb"
+                     else "bf16 scoring -> f32 accumulate, f32 re-rank",
+            "data": "synthetic",
             "config": dict(workload_config(args, wl, n_images, n_pairs), orb_engine=args.orb_engine) if kind == "orb" else workload_config(args, wl, n_images, n_pairs),
             "e2e": {"value": e2e_value, "unit": "pairs/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                     "steps": e2e_steps, "includes": "set_descriptors + commit (pinned staging, one H2D)" +

@@ -1,4 +1,6 @@
-// orb_kernels.cuh -- 256-bit ORB Hamming matching for sm_100a.
+// orb_kernels.cuh -- 256-bit ORB Hamming matching for sm_100a: the XOR+POPC engine (EACHAM_CFG_ORB_POPC) and the
+// single-direction kernels behind the reference-shaped Match()/knnMatch calls. (Batched ORB pairs default to the
+// tensor-core engine in tc_match_kernels.cuh, which returns the same bytes.)
 //
 // Replaces, for CV_8U 32-byte descriptors, what the reference does per unordered image pair:
 //   knnMatch(k=2) in both directions   /root/reference/modules/base/features/FeatureMatcherFlann.cpp:17
@@ -10,14 +12,15 @@
 //   * the 512 threads hold up to 8 rows each of the FIRST image in registers (4096 rows per row block);
 //   * the SECOND image streams through shared memory in 256-column chunks (8 KB, cp.async.bulk + mbarrier,
 //     double buffered); every thread reads the same column at the same time (broadcast LDS.128 x2);
-//   * each 256-bit distance is evaluated ONCE (8 LOP3 + 8 POPC + 4 IADD3) and feeds both directions:
+//   * each 256-bit distance is evaluated ONCE (8 XOR + 8 carry-save LOP3 + 4 POPC, see hamming256) and feeds both directions:
 //       row direction    -> packed key (d << 16 | column) into a per-row top-2 kept in registers,
 //       column direction -> packed key (d << 16 | row) into a per-thread top-2, reduced across the warp with
 //                           two REDUX.MIN, across the 16 warps through a shared-memory slot table;
 //     packed keys make "lowest index wins ties" (OpenCV batchDistance: strict <, ascending index) a plain min;
 //   * ratio test, gates, mutual filter and ordered compaction run in the same CTA; only surviving matches
 //     leave the chip.
-// The measured bound is the POPC pipe: 16 lane-ops/clk/SM (profiles/r01_pipe_microbench.jsonl).
+// POPC issues at 16 lane-ops/clk/SM (profiles/r01_pipe_microbench.jsonl); with the carry-save popcount the ALU pipe
+// (LOP3 + VIMNMX, 89 % busy) is the limiter: 44.4k pairs/s at 4k x 4k = 1.28 x the "8 POPC per distance" roofline.
 #pragma once
 #include <cstdint>
 #include <cuda_runtime.h>
