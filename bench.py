@@ -423,7 +423,18 @@ def main():
                 if ok and want["connected"]:
                     ok = np.array_equal(np.stack([got["query"], got["train"]], 1), want["matches"])
                 mism += (not ok)
-            cpu = {"value": v, "unit": "pairs/s", "cores": threads, "kind": "reference" if how == "reference-dependency" else "port",
+            one_thread = None
+            try:                                                  # also a 1-thread figure (3 pairs)
+                import cv2
+                cv2.setNumThreads(1)
+                t1 = time.perf_counter()
+                for k in list(cpu_res)[:3]:
+                    cpu_match_pair(images[int(all_pairs[k][0])], images[int(all_pairs[k][1])])
+                one_thread = 3 / (time.perf_counter() - t1)
+                cv2.setNumThreads(threads)
+            except Exception:
+                pass
+            cpu = {"value": v, "unit": "pairs/s", "cores": threads, "one_thread_value": one_thread, "kind": "reference" if how == "reference-dependency" else "port",
                    "sample": f"{n_s} random pairs of the workload (seed 123), OpenCV {('cv2 ' + __import__('cv2').__version__) if how == 'reference-dependency' else 'absent: C port'} "
                              f"batchDistance K=2 both directions + ratio + gates + mutual, {threads} threads",
                    "parity_checked_pairs": n_s, "parity_mismatches": mism}
