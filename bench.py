@@ -376,13 +376,15 @@ def main():
             achieved = work_per_pair * (len(my_pairs) * args.steps) / (float(sum(kernel_ms)) * 1e-3)
             traffic_path = os.path.join(ROOT, "profiles", "traffic.json")
             tkey = args.workload if args.orb_engine == "tensor" else args.workload + "_popc"
-            traffic = json.load(open(traffic_path)).get(tkey) if os.path.exists(traffic_path) else None
+            tj = json.load(open(traffic_path)) if os.path.exists(traffic_path) else {}
+            traffic = tj.get(tkey)
+            traffic_note = tj.get("_note")
             fp8_flops = 2.0 * 256 * n_desc * n_desc * (len(my_pairs) * args.steps) / (float(sum(kernel_ms)) * 1e-3)
             alu_ops_per_distance = 22.0        # 16 LOP3 + 6 VIMNMX issued on the ALU pipe per distance (SASS count)
             alu_peak = sm_count * 64.0 * pk["sm_max_mhz"] * 1e6
             alu_achieved = alu_ops_per_distance * n_desc * n_desc * (len(my_pairs) * args.steps) / (float(sum(kernel_ms)) * 1e-3)
             roof = {"bound": "int_popc", "achieved": achieved / 1e12, "peak": peak / 1e12, "unit": "TPOPC32/s",
-                    "frac": achieved / peak, "traffic": traffic,
+                    "frac": achieved / peak, "traffic": traffic, "traffic_note": traffic_note,
                     "peak_source": f"16.00 POPC lane-ops/clk/SM measured (profiles/r01_pipe_microbench.jsonl) x 148 SMs x sm_max_mhz "
                                    f"{pk['sm_max_mhz']:.0f} ({pk['_source']})",
                     "work_per_pair": work_per_pair, "kernel": "orb_match_pairs_kernel" if args.orb_engine == "popc" else "tc_match_pairs_kernel<orb>",
