@@ -59,7 +59,8 @@ def test_match_pairs_golden_tensor_core(matcher, sift_golden):
 
 
 @pytest.mark.parametrize("n1,n2,integer", [(1000, 1500, True), (300, 129, True), (257, 513, True), (128, 128, True), (1, 300, True),
-                                           (640, 2, True), (2048, 2048, True), (1200, 900, False), (2048, 2048, False)])
+                                           (640, 2, True), (2048, 2048, True), (1200, 900, False), (2048, 2048, False),
+                                           (8192, 8192, False)])
 def test_match_pairs_sizes_vs_opencv(matcher, n1, n2, integer):
     from eacham_b200 import synth
     n = max(n1, n2)
