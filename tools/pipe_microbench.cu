@@ -11,7 +11,7 @@
 constexpr int ITERS = 4096;
 constexpr int CHAINS = 8;
 
-enum Op { POPC, LOP3, IADD3, IMAD, VIMNMX, VIADDMNMX, REDUX, SHFL, MIX_DIST, MIX_DIST_TOP2 };
+enum Op { POPC, LOP3, IADD3, IMAD, VIMNMX, VIADDMNMX, REDUX, SHFL, MIX_DIST, MIX_DIST_TOP2, VIMNMX3, VIMNMX16X2, PRMT, FFMAIMM, HMNMX2 };
 
 template <int OP>
 __global__ void __launch_bounds__(1024, 1) bench(uint32_t* out, long long* cycles, uint32_t seed) {
@@ -33,6 +33,11 @@ __global__ void __launch_bounds__(1024, 1) bench(uint32_t* out, long long* cycle
             else if (OP == VIADDMNMX) a[i] = __viaddmin_u32(a[i], k, k2 + it);
             else if (OP == REDUX) asm volatile("redux.sync.min.u32 %0, %0, 0xffffffff;" : "+r"(a[i]));
             else if (OP == SHFL) asm volatile("shfl.sync.bfly.b32 %0, %0, 1, 0x1f, 0xffffffff;" : "+r"(a[i]));
+            else if (OP == VIMNMX3) a[i] = __vimin3_u32(a[i], k + it, k2 + i);
+            else if (OP == VIMNMX16X2) a[i] = __vminu2(a[i], k + i + it);
+            else if (OP == PRMT) asm volatile("prmt.b32 %0, %0, %1, 0x5410;" : "+r"(a[i]) : "r"(k + it));
+            else if (OP == FFMAIMM) a[i] = __float_as_uint(fmaf(__uint_as_float(a[i]), 1.0001f, 8388608.f));
+            else if (OP == HMNMX2) asm volatile("min.f16x2 %0, %0, %1;" : "+r"(a[i]) : "r"(k + i + it));
         }
     }
     long long t1 = clock64();
@@ -130,6 +135,11 @@ int main() {
         run<VIADDMNMX>("viaddmin", threads, out, cyc, nsm);
         run<REDUX>("redux_min", threads, out, cyc, nsm);
         run<SHFL>("shfl_bfly", threads, out, cyc, nsm);
+        run<VIMNMX3>("vimnmx3_u32", threads, out, cyc, nsm);
+        run<VIMNMX16X2>("vimnmx_u16x2", threads, out, cyc, nsm);
+        run<PRMT>("prmt", threads, out, cyc, nsm);
+        run<FFMAIMM>("ffma_imm", threads, out, cyc, nsm);
+        run<HMNMX2>("hmnmx2_f16x2", threads, out, cyc, nsm);
     }
     for (int top2 = 0; top2 < 2; ++top2) {
         int ncols = 4096;
