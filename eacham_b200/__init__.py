@@ -5,6 +5,7 @@ Only the hot path: kNN(k=2) + Lowe ratio + mutual cross-check over image pairs
 as hand-written sm_100a CUDA behind a C ABI (include/eacham_gpu.h). No CPU fallback.
 """
 from .matcher import FeatureMatcherGpu, PairMatches  # noqa: F401
+from .multi import MultiGpuMatcher  # noqa: F401
 from . import synth  # noqa: F401
 
-__all__ = ["FeatureMatcherGpu", "PairMatches", "synth"]
+__all__ = ["FeatureMatcherGpu", "MultiGpuMatcher", "PairMatches", "synth"]

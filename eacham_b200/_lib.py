@@ -5,15 +5,16 @@ import ctypes
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libeacham_gpu.so")
+LIB_PATH = os.environ.get("EACHAM_GPU_LIB") or os.path.join(_HERE, "libeacham_gpu.so")      # EACHAM_GPU_LIB: another BUILD of this library (kernel experiments)
 
 OK = 0
 ERR_INVALID_ARG, ERR_NO_DEVICE, ERR_CUDA, ERR_OUT_OF_MEMORY = -1, -2, -3, -4
-ERR_BUFFER_TOO_SMALL, ERR_NOT_COMMITTED, ERR_TOO_LARGE, ERR_KIND_MISMATCH = -5, -6, -7, -8
+ERR_BUFFER_TOO_SMALL, ERR_NOT_COMMITTED, ERR_TOO_LARGE, ERR_KIND_MISMATCH, ERR_NCCL = -5, -6, -7, -8, -9
 KIND_ORB256, KIND_F32X128 = 0, 1
 NONE = 0xFFFFFFFF
 PAIR_GATED, PAIR_CONNECTED = 1, 2
-CFG_SIFT_EXACT_FP32, CFG_ORB_POPC = 1, 2
+CFG_SIFT_EXACT_FP32, CFG_ORB_POPC, CFG_ORB_TC_V1, CFG_ORB_TC_ALU_SORT, CFG_MULTI_PARALLEL_H2D = 1, 2, 4, 8, 16
+ABI_VERSION = 2
 
 
 class Config(ctypes.Structure):
@@ -28,7 +29,13 @@ class MatchOpts(ctypes.Structure):
 
 class Timing(ctypes.Structure):
     _fields_ = [("upload_ms", ctypes.c_float), ("pairs_h2d_ms", ctypes.c_float), ("kernel_ms", ctypes.c_float),
-                ("d2h_ms", ctypes.c_float), ("kernel_launches", ctypes.c_uint32), ("reserved", ctypes.c_uint32)]
+                ("d2h_ms", ctypes.c_float), ("kernel_launches", ctypes.c_uint32), ("prep_ms", ctypes.c_float)]
+
+
+class MultiTiming(ctypes.Structure):
+    _fields_ = [("upload_ms", ctypes.c_float), ("broadcast_ms", ctypes.c_float), ("match_ms", ctypes.c_float), ("d2h_ms", ctypes.c_float),
+                ("kernel_ms_max", ctypes.c_float), ("prep_ms_max", ctypes.c_float), ("kernel_launches", ctypes.c_uint32),
+                ("reserved", ctypes.c_uint32)]
 
 
 # numpy-compatible record layouts of eacham_match_t / eacham_pair_t / eacham_pair_result_t
@@ -43,6 +50,9 @@ SYMBOLS = [
     "eacham_gpu_clear", "eacham_gpu_arena", "eacham_gpu_image_info", "eacham_gpu_match", "eacham_gpu_knn2",
     "eacham_gpu_match_pairs", "eacham_gpu_match_pairs_device", "eacham_gpu_fetch_results", "eacham_gpu_device_results", "eacham_gpu_last_timing",
     "eacham_gpu_flush_l2",
+    "eacham_gpu_create_multi", "eacham_gpu_destroy_multi", "eacham_gpu_multi_device_count", "eacham_gpu_multi_set_descriptors",
+    "eacham_gpu_multi_clear", "eacham_gpu_multi_commit", "eacham_gpu_multi_match_pairs", "eacham_gpu_multi_last_timing",
+    "eacham_gpu_host_alloc", "eacham_gpu_host_free",
 ]
 
 _lib = None
@@ -87,9 +97,23 @@ def load() -> ctypes.CDLL:
     lib.eacham_gpu_device_results.argtypes = [vp, P(vp), P(vp), P(sz), P(sz)]
     lib.eacham_gpu_last_timing.argtypes = [vp, P(Timing)]
     lib.eacham_gpu_flush_l2.argtypes = [vp, sz]
+    lib.eacham_gpu_create_multi.argtypes = [P(ctypes.c_int32), u32, P(Config), P(vp)]
+    lib.eacham_gpu_destroy_multi.argtypes = [vp]
+    lib.eacham_gpu_destroy_multi.restype = None
+    lib.eacham_gpu_multi_device_count.argtypes = [vp]
+    lib.eacham_gpu_multi_device_count.restype = u32
+    lib.eacham_gpu_multi_set_descriptors.argtypes = [vp, u32, i32, vp, u32, sz]
+    lib.eacham_gpu_multi_clear.argtypes = [vp]
+    lib.eacham_gpu_multi_commit.argtypes = [vp]
+    lib.eacham_gpu_multi_match_pairs.argtypes = [vp, vp, sz, P(MatchOpts), vp, vp, sz, P(sz)]
+    lib.eacham_gpu_multi_last_timing.argtypes = [vp, P(MultiTiming)]
+    lib.eacham_gpu_host_alloc.argtypes = [sz]
+    lib.eacham_gpu_host_alloc.restype = vp
+    lib.eacham_gpu_host_free.argtypes = [vp]
+    lib.eacham_gpu_host_free.restype = None
     for name in SYMBOLS:
         fn = getattr(lib, name)
-        if fn.restype is ctypes.c_int and name not in ("eacham_gpu_abi_version", "eacham_gpu_device_count"):
+        if fn.restype is ctypes.c_int and name not in ("eacham_gpu_abi_version", "eacham_gpu_device_count", "eacham_gpu_multi_device_count"):
             fn.restype = i32
     _lib = lib
     return lib

@@ -20,6 +20,7 @@
 #include "l2_kernels.cuh"
 #include "orb_kernels.cuh"
 #include "tc_match_kernels.cuh"
+#include "tc_orb_kernels.cuh"
 
 namespace {
 
@@ -52,7 +53,8 @@ struct ImageHost {
     uint32_t rows = 0;
     size_t offset = 0;     // byte offset in staging == arena
     bool present = false;
-    bool has_data = false;
+    bool has_data = false;   // bytes staged by set_descriptors
+    bool reserved = false;   // shape declared by reserve: bytes arrive in the device arena by broadcast
 };
 
 template <typename T>
@@ -83,7 +85,7 @@ struct eacham_gpu_handle {
 
     std::vector<ImageHost> images;
     uint8_t* staging = nullptr;   // pinned
-    size_t staging_cap = 0, staging_used = 0;
+    size_t staging_cap = 0, staging_used = 0, staging_waste = 0;
     bool committed = false;
     bool any_data = false;
 
@@ -94,6 +96,7 @@ struct eacham_gpu_handle {
     // SIFT tensor-core path: pre-tiled bf16 copy of every F32X128 image, built lazily after commit (+ broadcast)
     DevBuf<uint8_t> tc_arena;
     DevBuf<eacham::tcm::ImageDescTc> d_images_tc;
+    DevBuf<uint32_t> d_block_start;
     std::vector<size_t> tc_offsets;
     size_t tc_bytes = 0;
     bool tc_dirty = true;
@@ -134,30 +137,56 @@ int ensure_staging(eacham_gpu_handle* h, size_t need) {
     size_t cap = std::max(need, std::max(h->staging_cap * 2, (size_t)1 << 20));
     uint8_t* n = nullptr;
     CUDA_TRY(cudaMallocHost(&n, cap));
-    if (h->staging) { memcpy(n, h->staging, h->staging_used); cudaFreeHost(h->staging); }
+    if (h->staging) { memcpy(n, h->staging, std::min(h->staging_used, h->staging_cap)); cudaFreeHost(h->staging); }
     h->staging = n; h->staging_cap = cap;
     return EACHAM_OK;
 }
 
-int place_image(eacham_gpu_handle* h, uint32_t image_id, int kind, uint32_t rows, bool& reuse) {
+// Gives image_id a region of the arena layout. Only set_descriptors backs the layout with pinned staging memory
+// (`backed`); reserve just computes offsets. A region whose image changes size is abandoned and reclaimed by the
+// compaction in commit.
+int place_image(eacham_gpu_handle* h, uint32_t image_id, int kind, uint32_t rows, bool backed) {
     if (kind != EACHAM_KIND_ORB256 && kind != EACHAM_KIND_F32X128) return fail(EACHAM_ERR_INVALID_ARG, "unknown descriptor kind %d", kind);
     if (rows > 65535u) return fail(EACHAM_ERR_TOO_LARGE, "image %u has %u descriptors; at most 65535 are supported", image_id, rows);
-    if (image_id >= h->images.size()) {
-        if (image_id > (1u << 26)) return fail(EACHAM_ERR_INVALID_ARG, "image id %u out of range", image_id);
-        h->images.resize((size_t)image_id + 1);
-    }
-    ImageHost& im = h->images[image_id];
-    reuse = im.present && im.kind == kind && im.rows == rows;
-    if (!reuse) {
-        im.offset = align_up(h->staging_used, kAlign);
-        size_t end = im.offset + (size_t)rows * row_bytes(kind);
-        int rc = ensure_staging(h, align_up(end, kAlign));
+    if (image_id > (1u << 26)) return fail(EACHAM_ERR_INVALID_ARG, "image id %u out of range", image_id);
+    const bool known = image_id < h->images.size() && h->images[image_id].present;
+    const bool reuse = known && h->images[image_id].kind == kind && h->images[image_id].rows == rows;
+    size_t offset = reuse ? h->images[image_id].offset : align_up(h->staging_used, kAlign);
+    const size_t end = offset + (size_t)rows * row_bytes(kind);
+    if (backed) {
+        int rc = ensure_staging(h, align_up(std::max(end, h->staging_used), kAlign));
         if (rc) return rc;
+    }
+    if (image_id >= h->images.size()) h->images.resize((size_t)image_id + 1);
+    ImageHost& im = h->images[image_id];
+    if (!reuse) {
+        if (known) h->staging_waste += align_up((size_t)im.rows * row_bytes(im.kind), kAlign);
+        im.offset = offset;
         h->staging_used = end;
-        im.kind = kind; im.rows = rows; im.present = true; im.has_data = false;
+        im.kind = kind; im.rows = rows; im.present = true; im.has_data = false; im.reserved = false;
     }
     h->committed = false;
     return EACHAM_OK;
+}
+
+// Re-packs the staged images in id order so that abandoned regions (images re-set with another row count) do not
+// accumulate; only possible while every image's bytes are still in staging (no reserved images).
+void compact_staging(eacham_gpu_handle* h) {
+    if (h->staging_waste == 0) return;
+    for (const ImageHost& im : h->images) if (im.present && im.reserved) return;
+    std::vector<uint32_t> order;
+    for (uint32_t i = 0; i < h->images.size(); ++i) if (h->images[i].present) order.push_back(i);
+    std::sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) { return h->images[a].offset < h->images[b].offset; });
+    size_t used = 0;
+    for (uint32_t i : order) {
+        ImageHost& im = h->images[i];
+        const size_t off = align_up(used, kAlign), bytes = (size_t)im.rows * row_bytes(im.kind);
+        if (off != im.offset && im.has_data && bytes) memmove(h->staging + off, h->staging + im.offset, bytes);
+        im.offset = off;
+        used = off + bytes;
+    }
+    h->staging_used = used;
+    h->staging_waste = 0;
 }
 
 }  // namespace
@@ -199,8 +228,8 @@ int eacham_gpu_create(const eacham_gpu_config* cfg, eacham_gpu_handle** out) {
     DeviceGuard g(dev);
     cudaError_t e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking);
     for (int i = 0; i < 8 && e == cudaSuccess; ++i) e = cudaEventCreate(&h->ev[i]);
-    if (e != cudaSuccess) { delete h; return fail(EACHAM_ERR_CUDA, "stream/event creation failed: %s", cudaGetErrorString(e)); }
-    if (h->d_counter.ensure(16) || h->d_cursor.ensure(16)) { delete h; return EACHAM_ERR_OUT_OF_MEMORY; }
+    if (e != cudaSuccess) { eacham_gpu_destroy(h); return fail(EACHAM_ERR_CUDA, "stream/event creation failed: %s", cudaGetErrorString(e)); }
+    if (h->d_counter.ensure(16) || h->d_cursor.ensure(16)) { eacham_gpu_destroy(h); return EACHAM_ERR_OUT_OF_MEMORY; }
     *out = h;
     return EACHAM_OK;
 }
@@ -209,8 +238,8 @@ void eacham_gpu_destroy(eacham_gpu_handle* h) {
     if (!h) return;
     {
         DeviceGuard g(h->device);
-        cudaStreamSynchronize(h->stream);
-        h->tc_arena.release(); h->d_images_tc.release(); h->tc_scratch.release();
+        if (h->stream) cudaStreamSynchronize(h->stream);
+        h->tc_arena.release(); h->d_images_tc.release(); h->d_block_start.release(); h->tc_scratch.release();
         h->arena.release(); h->d_images.release(); h->d_pairs.release(); h->d_results.release(); h->d_matches.release();
         h->d_counter.release(); h->d_cursor.release(); h->d_q.release(); h->d_t.release(); h->d_partial.release();
         h->d_idx.release(); h->d_dist.release(); h->d_match.release(); h->d_match2.release(); h->d_flush.release();
@@ -224,19 +253,19 @@ void eacham_gpu_destroy(eacham_gpu_handle* h) {
 int eacham_gpu_set_descriptors(eacham_gpu_handle* h, uint32_t image_id, int kind, const void* data, uint32_t rows,
                                size_t row_stride_bytes) {
     if (!h) return fail(EACHAM_ERR_INVALID_ARG, "null handle");
+    if (kind != EACHAM_KIND_ORB256 && kind != EACHAM_KIND_F32X128) return fail(EACHAM_ERR_INVALID_ARG, "unknown descriptor kind %d", kind);
     if (rows > 0 && !data) return fail(EACHAM_ERR_INVALID_ARG, "null descriptor pointer for image %u", image_id);
-    std::lock_guard<std::mutex> lk(h->mu);
-    DeviceGuard g(h->device);
-    bool reuse = false;
-    int rc = place_image(h, image_id, kind, rows, reuse);
-    if (rc) return rc;
     const size_t rb = row_bytes(kind);
     if (rows > 0 && row_stride_bytes < rb) return fail(EACHAM_ERR_INVALID_ARG, "row stride %zu < row size %zu", row_stride_bytes, rb);
+    std::lock_guard<std::mutex> lk(h->mu);
+    DeviceGuard g(h->device);
+    int rc = place_image(h, image_id, kind, rows, /*backed=*/true);       // nothing is modified when this fails
+    if (rc) return rc;
     ImageHost& im = h->images[image_id];
     uint8_t* dst = h->staging + im.offset;
     if (row_stride_bytes == rb) memcpy(dst, data, (size_t)rows * rb);
     else for (uint32_t r = 0; r < rows; ++r) memcpy(dst + (size_t)r * rb, (const uint8_t*)data + (size_t)r * row_stride_bytes, rb);
-    im.has_data = true;
+    im.has_data = true; im.reserved = false;
     h->any_data = true;
     return EACHAM_OK;
 }
@@ -245,15 +274,17 @@ int eacham_gpu_reserve(eacham_gpu_handle* h, uint32_t image_id, int kind, uint32
     if (!h) return fail(EACHAM_ERR_INVALID_ARG, "null handle");
     std::lock_guard<std::mutex> lk(h->mu);
     DeviceGuard g(h->device);
-    bool reuse = false;
-    return place_image(h, image_id, kind, rows, reuse);
+    int rc = place_image(h, image_id, kind, rows, /*backed=*/false);
+    if (rc) return rc;
+    h->images[image_id].reserved = true; h->images[image_id].has_data = false;
+    return EACHAM_OK;
 }
 
 int eacham_gpu_clear(eacham_gpu_handle* h) {
     if (!h) return fail(EACHAM_ERR_INVALID_ARG, "null handle");
     std::lock_guard<std::mutex> lk(h->mu);
     h->images.clear();
-    h->staging_used = 0; h->committed = false; h->any_data = false; h->arena_bytes = 0;
+    h->staging_used = 0; h->staging_waste = 0; h->committed = false; h->any_data = false; h->arena_bytes = 0;
     h->max_rows[0] = h->max_rows[1] = 0;
     return EACHAM_OK;
 }
@@ -262,6 +293,7 @@ int eacham_gpu_commit(eacham_gpu_handle* h) {
     if (!h) return fail(EACHAM_ERR_INVALID_ARG, "null handle");
     std::lock_guard<std::mutex> lk(h->mu);
     DeviceGuard g(h->device);
+    compact_staging(h);
     const size_t bytes = align_up(std::max(h->staging_used, (size_t)1), kAlign);
     int rc = h->arena.ensure(bytes + kAlign);
     if (rc) return rc;
@@ -286,8 +318,10 @@ int eacham_gpu_commit(eacham_gpu_handle* h) {
     }
     h->tc_dirty = true;
     CUDA_TRY(cudaEventRecord(h->ev[0], h->stream));
-    if (h->any_data && h->staging_used > 0)
-        CUDA_TRY(cudaMemcpyAsync(h->arena.p, h->staging, h->staging_used, cudaMemcpyHostToDevice, h->stream));
+    // one H2D copy of everything staged (ranges of reserved images carry no host bytes: a broadcast fills them)
+    const size_t staged = std::min(h->staging_used, h->staging_cap);
+    if (h->any_data && staged > 0)
+        CUDA_TRY(cudaMemcpyAsync(h->arena.p, h->staging, staged, cudaMemcpyHostToDevice, h->stream));
     if (!table.empty())
         CUDA_TRY(cudaMemcpyAsync(h->d_images.p, table.data(), table.size() * sizeof(table[0]), cudaMemcpyHostToDevice, h->stream));
     CUDA_TRY(cudaEventRecord(h->ev[1], h->stream));
@@ -452,32 +486,41 @@ int eacham_gpu_match(eacham_gpu_handle* h, int kind, const void* query, uint32_t
 // -------------------------------------------------------------------------------------------------------------
 namespace {
 
-// Builds the pre-tiled bf16 copy (tc_common.cuh layout) of every F32X128 image from the fp32 arena. Runs lazily at the
-// first SIFT match_pairs after a commit, i.e. after a possible NCCL broadcast has filled the arena on this rank.
+// Builds the tensor-core copy (tc_common.cuh block layout) of every image that has one -- bf16 for F32X128, one e4m3 element
+// per bit for ORB256 -- from the raw arena, in ONE launch over the image table. Runs lazily at the first match_pairs after a
+// commit, i.e. after a possible NCCL broadcast has filled the arena on this device. Timed into timing.prep_ms.
 int prepare_tc(eacham_gpu_handle* h) {
     using namespace eacham;
     if (!h->tc_dirty) return EACHAM_OK;
     int rc;
     if ((rc = h->tc_arena.ensure(std::max(h->tc_bytes, (size_t)tc::kBlockBytes)))) return rc;
     if ((rc = h->d_images_tc.ensure(std::max(h->images.size(), (size_t)1)))) return rc;
+    if ((rc = h->d_block_start.ensure(h->images.size() + 1))) return rc;
     std::vector<tcm::ImageDescTc> table(h->images.size());
+    std::vector<uint32_t> block_start(h->images.size() + 1, 0);
+    uint32_t blocks = 0;
     for (size_t i = 0; i < h->images.size(); ++i) {
         const ImageHost& im = h->images[i];
         table[i].offset = im.offset; table[i].tc_offset = h->tc_offsets[i];
         table[i].rows = im.present ? im.rows : 0; table[i].kind = im.present ? (uint32_t)im.kind : 0xffffffffu;
-        if (im.present && im.rows > 0) {
-            const uint32_t nblk = (im.rows + 127) / 128;
-            if (im.kind == EACHAM_KIND_F32X128)
-                tcm::sift_prep_kernel<<<nblk * 16, 256, 0, h->stream>>>(reinterpret_cast<const float*>(h->arena.p + im.offset), im.rows,
-                                                                          h->tc_arena.p + h->tc_offsets[i], nblk);
-            else if (!(h->cfg_flags & EACHAM_CFG_ORB_POPC))
-                tcm::orb_tc_prep_kernel<<<nblk * 16, 256, 0, h->stream>>>(h->arena.p + im.offset, im.rows, h->tc_arena.p + h->tc_offsets[i], nblk);
-        }
+        block_start[i] = blocks;
+        const bool has_tc = im.present && im.rows > 0 && (im.kind == EACHAM_KIND_F32X128 || !(h->cfg_flags & EACHAM_CFG_ORB_POPC));
+        if (has_tc) blocks += (im.rows + 127) / 128;
     }
-    CUDA_TRY(cudaGetLastError());
-    if (!table.empty())
+    block_start[h->images.size()] = blocks;
+    CUDA_TRY(cudaEventRecord(h->ev[0], h->stream));
+    if (!table.empty()) {
         CUDA_TRY(cudaMemcpyAsync(h->d_images_tc.p, table.data(), table.size() * sizeof(table[0]), cudaMemcpyHostToDevice, h->stream));
-    CUDA_TRY(cudaStreamSynchronize(h->stream));
+        CUDA_TRY(cudaMemcpyAsync(h->d_block_start.p, block_start.data(), block_start.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, h->stream));
+    }
+    if (blocks > 0) {
+        tcm::tc_prep_all_kernel<<<blocks * 16, 256, 0, h->stream>>>(h->arena.p, h->tc_arena.p, h->d_images_tc.p, h->d_block_start.p,
+                                                                     (uint32_t)h->images.size());
+        CUDA_TRY(cudaGetLastError());
+    }
+    CUDA_TRY(cudaEventRecord(h->ev[1], h->stream));
+    CUDA_TRY(cudaStreamSynchronize(h->stream));               // the host tables above go out of scope
+    CUDA_TRY(cudaEventElapsedTime(&h->timing.prep_ms, h->ev[0], h->ev[1]));
     h->tc_dirty = false;
     return EACHAM_OK;
 }
@@ -490,7 +533,7 @@ int launch_pairs(eacham_gpu_handle* h, const eacham_pair_t* pairs, size_t n_pair
     if (opts_in) o = *opts_in; else eacham_gpu_default_opts(&o);
     h->timing.kernel_launches = 0;
     h->timing.kernel_ms = h->timing.pairs_h2d_ms = h->timing.d2h_ms = 0.f;
-    h->last_n_pairs = n_pairs;
+    h->last_n_pairs = 0;                 // a failed call leaves nothing to fetch
     h->last_total = 0;
     if (n_pairs == 0) return EACHAM_OK;
 
@@ -501,6 +544,8 @@ int launch_pairs(eacham_gpu_handle* h, const eacham_pair_t* pairs, size_t n_pair
         const uint32_t a = pairs[i].first, b = pairs[i].second;
         if (a >= h->images.size() || b >= h->images.size() || !h->images[a].present || !h->images[b].present)
             return fail(EACHAM_ERR_NOT_COMMITTED, "pair %zu = (%u, %u) names an image without descriptors", i, a, b);
+        if (!(h->images[a].has_data || h->images[a].reserved) || !(h->images[b].has_data || h->images[b].reserved))
+            return fail(EACHAM_ERR_NOT_COMMITTED, "pair %zu = (%u, %u) names an image whose descriptors were never set", i, a, b);
         if (kind < 0) kind = h->images[a].kind;
         if (h->images[a].kind != kind || h->images[b].kind != kind)
             return fail(EACHAM_ERR_KIND_MISMATCH, "pair %zu = (%u, %u) mixes descriptor kinds", i, a, b);
@@ -515,8 +560,10 @@ int launch_pairs(eacham_gpu_handle* h, const eacham_pair_t* pairs, size_t n_pair
                                                : std::max((size_t)1 << 20, n_pairs * (size_t)192);
     if (h->d_matches.cap < want_entries && (rc = h->d_matches.ensure(want_entries))) return rc;
 
+    // The tensor-core ORB engines keep no indices in their hot loop; they rely on a match being a strict unique minimum, which
+    // holds for ratio <= 1. A ratio above 1 (ties can pass) goes to the XOR+POPC kernels, whose packed keys carry OpenCV's tie order.
     const bool use_tc = (kind == EACHAM_KIND_F32X128 && !(h->cfg_flags & EACHAM_CFG_SIFT_EXACT_FP32)) ||
-                        (kind == EACHAM_KIND_ORB256 && !(h->cfg_flags & EACHAM_CFG_ORB_POPC));
+                        (kind == EACHAM_KIND_ORB256 && !(h->cfg_flags & EACHAM_CFG_ORB_POPC) && o.ratio <= 1.0);
     if (use_tc && (rc = prepare_tc(h))) return rc;
     CUDA_TRY(cudaEventRecord(h->ev[2], h->stream));
     CUDA_TRY(cudaMemcpyAsync(h->d_pairs.p, pairs, n_pairs * sizeof(eacham_pair_t), cudaMemcpyHostToDevice, h->stream));
@@ -552,8 +599,19 @@ int launch_pairs(eacham_gpu_handle* h, const eacham_pair_t* pairs, size_t n_pair
             const unsigned grid = (unsigned)std::min<size_t>(n_pairs, (size_t)h->sm_count);
             if ((rc = h->tc_scratch.ensure(tcm::tc_scratch_bytes_per_cta(p.rows_cap, p.cols_cap) * grid))) return rc;
             p.scratch = h->tc_scratch.p;
+            p.work_counter = h->d_counter.p;
             const size_t smem = sizeof(tcm::SmemTc) + 128;
-            if (kind == EACHAM_KIND_ORB256) {
+            if (kind == EACHAM_KIND_ORB256 && !(h->cfg_flags & EACHAM_CFG_ORB_TC_V1)) {
+                // default: F16 accumulators, packed epilogue (tc_orb_kernels.cuh)
+                const size_t smem2 = sizeof(tco::SmemOrb) + 128;
+                if (h->cfg_flags & EACHAM_CFG_ORB_TC_ALU_SORT) {
+                    CUDA_TRY(cudaFuncSetAttribute(tco::orb_tc_match_pairs_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
+                    tco::orb_tc_match_pairs_kernel<false><<<grid, tco::kThreads, smem2, h->stream>>>(p);
+                } else {
+                    CUDA_TRY(cudaFuncSetAttribute(tco::orb_tc_match_pairs_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
+                    tco::orb_tc_match_pairs_kernel<true><<<grid, tco::kThreads, smem2, h->stream>>>(p);
+                }
+            } else if (kind == EACHAM_KIND_ORB256) {
                 CUDA_TRY(cudaFuncSetAttribute(tcm::tc_match_pairs_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
                 tcm::tc_match_pairs_kernel<true><<<grid, tcm::kThreadsTc, smem, h->stream>>>(p);
             } else {
@@ -586,13 +644,13 @@ int launch_pairs(eacham_gpu_handle* h, const eacham_pair_t* pairs, size_t n_pair
         unsigned long long used = 0;
         CUDA_TRY(cudaMemcpyAsync(&used, h->d_cursor.p, sizeof(used), cudaMemcpyDeviceToHost, h->stream));
         CUDA_TRY(cudaStreamSynchronize(h->stream));
-        h->last_total = used;
-        if (used <= h->d_matches.cap) break;
+        if (used <= h->d_matches.cap) { h->last_total = used; break; }
         if (attempt == 1) return fail(EACHAM_ERR_OUT_OF_MEMORY, "match buffer overflow persisted after regrow");
         if ((rc = h->d_matches.ensure((size_t)used + 1024))) return rc;   // deterministic need: rerun once
     }
     CUDA_TRY(cudaEventElapsedTime(&h->timing.pairs_h2d_ms, h->ev[2], h->ev[3]));
     CUDA_TRY(cudaEventElapsedTime(&h->timing.kernel_ms, h->ev[4], h->ev[5]));
+    h->last_n_pairs = n_pairs;           // only a completed batch can be fetched
     return EACHAM_OK;
 }
 
@@ -602,7 +660,7 @@ int fetch(eacham_gpu_handle* h, eacham_pair_result_t* res, size_t n_pairs, eacha
     if (n_pairs == 0) return EACHAM_OK;
     CUDA_TRY(cudaEventRecord(h->ev[6], h->stream));
     if (res) CUDA_TRY(cudaMemcpyAsync(res, h->d_results.p, n_pairs * sizeof(eacham_pair_result_t), cudaMemcpyDeviceToHost, h->stream));
-    const size_t n_copy = std::min((size_t)h->last_total, buf_cap);
+    const size_t n_copy = std::min(std::min((size_t)h->last_total, buf_cap), h->d_matches.cap);
     if (buf && n_copy) CUDA_TRY(cudaMemcpyAsync(buf, h->d_matches.p, n_copy * sizeof(eacham_match_t), cudaMemcpyDeviceToHost, h->stream));
     CUDA_TRY(cudaEventRecord(h->ev[7], h->stream));
     CUDA_TRY(cudaStreamSynchronize(h->stream));
@@ -654,3 +712,5 @@ int eacham_gpu_match_pairs(eacham_gpu_handle* h, const eacham_pair_t* pairs, siz
 }
 
 }  // extern "C"
+
+#include "multi.cuh"

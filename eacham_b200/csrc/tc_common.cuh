@@ -49,6 +49,19 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t by
                  ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
 
+// One lane of a CONVERGED warp. Code that issues uniform-datapath instructions (tcgen05.mma / commit, bulk copies) must sit under
+// this predicate inside warp-uniform control flow: under a plain `if (lane == 0)` the compiler cannot prove uniformity and wraps
+// every such instruction in a waterfall loop (ELECT + BRA.U.ANY in SASS), which made each MMA cost ~80-110 issue cycles.
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "elect.sync _|p, 0xffffffff;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(pred));
+    return pred != 0;
+}
+
 // ---- tensor memory ----------------------------------------------------------------------------------------
 // One full warp allocates `cols` (power of two >= 32) TMEM columns; the base address lands in *slot (smem).
 __device__ __forceinline__ void tmem_alloc(uint32_t* slot, uint32_t cols) {
@@ -80,9 +93,10 @@ __device__ __forceinline__ void mma_bf16(uint32_t tmem_d, uint64_t desc_a, uint6
         ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate) : "memory");
 }
 // FP8 (e4m3 x e4m3 -> f32) variant: one K=32 step (32 bytes per row, i.e. the same two 16-byte K-chunks as a bf16 K=16 step)
-__host__ __device__ constexpr uint32_t make_idesc_e4m3_f32(uint32_t m, uint32_t n, bool negate_a) {
-    return (1u << 4) | ((negate_a ? 1u : 0u) << 13) | ((n >> 3) << 17) | ((m >> 4) << 24);      // A/B format 0 = E4M3
+__host__ __device__ constexpr uint32_t make_idesc_e4m3(uint32_t m, uint32_t n, bool negate_a, bool d_f32) {
+    return ((d_f32 ? 1u : 0u) << 4) | ((negate_a ? 1u : 0u) << 13) | ((n >> 3) << 17) | ((m >> 4) << 24);   // A/B format 0 = E4M3; D format 0 = F16, 1 = F32
 }
+__host__ __device__ constexpr uint32_t make_idesc_e4m3_f32(uint32_t m, uint32_t n, bool negate_a) { return make_idesc_e4m3(m, n, negate_a, true); }
 __device__ __forceinline__ void mma_f8(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
     asm volatile(
         "{\n\t.reg .pred p;\n\t"

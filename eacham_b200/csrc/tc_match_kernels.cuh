@@ -30,11 +30,7 @@ __device__ __forceinline__ void split3(float x, __nv_bfloat16& hi, __nv_bfloat16
 
 // fp32 rows [rows][128] -> pre-tiled bf16 blocks (tc_common.cuh layout). One warp per row; grid covers
 // n_blocks * 128 rows (rows >= `rows` are padding: zero data, norm 1e30 so they never win a minimum).
-__global__ void __launch_bounds__(256) sift_prep_kernel(const float* __restrict__ src, uint32_t rows, uint8_t* __restrict__ dst,
-                                                        uint32_t n_blocks) {
-    const uint32_t row = blockIdx.x * 8 + (threadIdx.x >> 5);
-    const int lane = threadIdx.x & 31;
-    if (row >= n_blocks * tc::kBlockRows) return;
+__device__ __forceinline__ void sift_prep_row(const float* __restrict__ src, uint32_t rows, uint8_t* __restrict__ dst, uint32_t row, int lane) {
     uint8_t* blk = dst + (size_t)(row / tc::kBlockRows) * tc::kBlockBytes;
     const uint32_t r = row % tc::kBlockRows;
     float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -77,11 +73,7 @@ __global__ void __launch_bounds__(256) sift_prep_kernel(const float* __restrict_
 // into three exactly representable e4m3 pieces (16*(n>>5), (n>>1)&15, (n&1)/2) and three ones. For 0/1 vectors
 // |a-b|^2 = popcount(a xor b), so with negate-A the FP8 MMA yields D = hamming(a,b)/2 EXACTLY (all partial sums are small
 // multiples of 1/2). This is the default engine for ORB pairs; EACHAM_CFG_ORB_POPC selects the XOR+POPC kernel (orb_kernels.cuh) instead.
-__global__ void __launch_bounds__(256) orb_tc_prep_kernel(const uint8_t* __restrict__ src, uint32_t rows, uint8_t* __restrict__ dst,
-                                                          uint32_t n_blocks) {
-    const uint32_t row = blockIdx.x * 8 + (threadIdx.x >> 5);
-    const int lane = threadIdx.x & 31;
-    if (row >= n_blocks * tc::kBlockRows) return;
+__device__ __forceinline__ void orb_tc_prep_row(const uint8_t* __restrict__ src, uint32_t rows, uint8_t* __restrict__ dst, uint32_t row, int lane) {
     uint8_t* blk = dst + (size_t)(row / tc::kBlockRows) * tc::kBlockBytes;
     const uint32_t r = row % tc::kBlockRows;
     const uint32_t byte = (row < rows) ? (uint32_t)__ldg(src + (size_t)row * 32 + lane) : 0u;
@@ -112,6 +104,43 @@ __global__ void __launch_bounds__(256) orb_tc_prep_kernel(const uint8_t* __restr
     }
 }
 
+// one image at a time (tools / unit tests); grid covers n_blocks * 128 rows, one warp per row
+__global__ void __launch_bounds__(256) sift_prep_kernel(const float* __restrict__ src, uint32_t rows, uint8_t* __restrict__ dst,
+                                                        uint32_t n_blocks) {
+    const uint32_t row = blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (row < n_blocks * tc::kBlockRows) sift_prep_row(src, rows, dst, row, threadIdx.x & 31);
+}
+__global__ void __launch_bounds__(256) orb_tc_prep_kernel(const uint8_t* __restrict__ src, uint32_t rows, uint8_t* __restrict__ dst,
+                                                          uint32_t n_blocks) {
+    const uint32_t row = blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (row < n_blocks * tc::kBlockRows) orb_tc_prep_row(src, rows, dst, row, threadIdx.x & 31);
+}
+
+struct ImageDescTc {
+    unsigned long long offset;      // raw rows in the arena (fp32 x 128 or 32 bytes)
+    unsigned long long tc_offset;   // pre-tiled blocks in the tc arena
+    uint32_t rows;
+    uint32_t kind;
+};
+
+// The whole image table in ONE launch: CTA b handles 8 rows of 128-row block b / 16; block_start[i] = first block of image i
+// (prefix sums, n_images + 1 entries; images without a tensor-core copy have an empty range).
+__global__ void __launch_bounds__(256) tc_prep_all_kernel(const uint8_t* __restrict__ arena, uint8_t* __restrict__ tc_arena,
+                                                          const ImageDescTc* __restrict__ images, const uint32_t* __restrict__ block_start,
+                                                          uint32_t n_images) {
+    const uint32_t blk = blockIdx.x / 16;
+    uint32_t lo = 0, hi = n_images;                     // last image with block_start[i] <= blk
+    while (hi - lo > 1) {
+        const uint32_t mid = (lo + hi) >> 1;
+        if (__ldg(block_start + mid) <= blk) lo = mid; else hi = mid;
+    }
+    const ImageDescTc im = images[lo];
+    const uint32_t row = (blk - __ldg(block_start + lo)) * tc::kBlockRows + (blockIdx.x % 16) * 8 + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (im.kind == EACHAM_KIND_F32X128) sift_prep_row(reinterpret_cast<const float*>(arena + im.offset), im.rows, tc_arena + im.tc_offset, row, lane);
+    else orb_tc_prep_row(arena + im.offset, im.rows, tc_arena + im.tc_offset, row, lane);
+}
+
 // =============================================================================================================
 // The fused SIFT pair kernel.
 //
@@ -130,13 +159,6 @@ __global__ void __launch_bounds__(256) orb_tc_prep_kernel(const uint8_t* __restr
 // fp32 rows, the ratio test is applied, and at the end of the pair the same happens for columns, followed by the
 // reference's gates / mutual filter / compaction -- all inside the CTA.
 // =============================================================================================================
-struct ImageDescTc {
-    unsigned long long offset;      // fp32 rows in the arena
-    unsigned long long tc_offset;   // pre-tiled bf16 blocks in the tc arena
-    uint32_t rows;
-    uint32_t kind;
-};
-
 struct PairParamsTc {
     const uint8_t* arena;           // fp32 descriptors (exact re-rank)
     const uint8_t* tc_arena;        // bf16 blocks (scoring)
@@ -151,6 +173,7 @@ struct PairParamsTc {
     unsigned long long* cursor;
     uint8_t* scratch;               // per CTA: colstate (16 B x cols_cap) + m12 (4 B x rows_cap) + m21 (4 B x cols_cap)
     uint32_t rows_cap, cols_cap;    // multiples of 128
+    uint32_t* work_counter;         // dynamic pair queue (zeroed by the host before the launch)
 };
 
 constexpr int kEpiWarps = 16;          // 4 per TMEM lane quadrant, 32 columns of every tile each
@@ -165,7 +188,7 @@ constexpr int32_t kEmptyKeyTc = 0x7F7FFF00;
 constexpr long long kEmptyComp = ((long long)0x7F7FFF << 32) | 0xFFFFFFFFll;
 
 __host__ __device__ inline size_t tc_scratch_bytes_per_cta(uint32_t rows_cap, uint32_t cols_cap) {
-    return (size_t)cols_cap * 16 + (size_t)rows_cap * 4 + (size_t)cols_cap * 4;
+    return (size_t)cols_cap * 32 + (size_t)rows_cap * 4 + (size_t)cols_cap * 4;      // column state (16 B SIFT / 32 B ORB per column) + m12 + m21
 }
 
 struct SmemTc {
@@ -304,6 +327,70 @@ __device__ __forceinline__ void epi_tile(uint32_t acc_taddr, int cp, int q, int 
             slot_q[cp * kColsPerWarp + idx] = make_uint2((uint32_t)g0, (uint32_t)g1);   // warp-uniform value: all lanes store the same word
         }
     }
+}
+
+// Gates, mutual filter and ordered compaction of one pair (/root/reference/apps/sfm/main.cpp:111-146), run by the 512
+// epilogue threads of a CTA once m12[0..N) / m21[0..M) hold the ratio-filtered matches of both directions (EACHAM_NONE = no
+// match). S needs `red[2 * kEpiWarps + 8]` and `base`. Ends with an epilogue barrier (scratch reusable).
+template <class Smem>
+__device__ __forceinline__ void gates_mutual_compact(Smem& S, const PairParamsTc& p, uint32_t pi, uint32_t N, uint32_t M,
+                                                     const uint32_t* __restrict__ m12, const uint32_t* __restrict__ m21, int et, int e, int lane) {
+    uint32_t c12 = 0, c21 = 0;
+    for (uint32_t i = et; i < N; i += kEpiThreads) c12 += m12[i] != EACHAM_NONE;
+    for (uint32_t j = et; j < M; j += kEpiThreads) c21 += m21[j] != EACHAM_NONE;
+    c12 = __reduce_add_sync(0xffffffffu, c12);
+    c21 = __reduce_add_sync(0xffffffffu, c21);
+    if (lane == 0) { S.red[e] = c12; S.red[kEpiWarps + e] = c21; }
+    epi_bar();
+    uint32_t n12 = 0, n21 = 0;
+#pragma unroll
+    for (int w = 0; w < kEpiWarps; ++w) { n12 += S.red[w]; n21 += S.red[kEpiWarps + w]; }
+    const bool gated = p.cross_check ? (n12 < p.min_dir || n21 < p.min_dir) : (n12 < p.min_dir);
+    const uint32_t per = (N + kEpiThreads - 1) / kEpiThreads;
+    const uint32_t lo = min(N, et * per), hi = min(N, lo + per);
+    uint32_t mine = 0;
+    if (!gated)
+        for (uint32_t a = lo; a < hi; ++a) {
+            const uint32_t b = m12[a];
+            mine += (b != EACHAM_NONE) && (!p.cross_check || m21[b] == a);
+        }
+    uint32_t incl = mine;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t v = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += v;
+    }
+    epi_bar();
+    if (lane == 31) S.red[e] = incl;
+    epi_bar();
+    uint32_t woff = 0, total = 0;
+#pragma unroll
+    for (int w = 0; w < kEpiWarps; ++w) { if (w < e) woff += S.red[w]; total += S.red[w]; }
+    const uint32_t excl = woff + incl - mine;
+    const bool connected = !gated && total > p.min_mutual;
+    const bool emit = !gated && (connected || p.emit_all) && total > 0;
+    if (et == 0) {
+        unsigned long long base = 0;
+        if (emit) base = atomicAdd(p.cursor, (unsigned long long)total);
+        S.base = base;
+        eacham_pair_result_t r;
+        r.n12 = n12; r.n21 = n21; r.n_mutual = gated ? 0u : total;
+        r.flags = (gated ? EACHAM_PAIR_GATED : 0u) | (connected ? EACHAM_PAIR_CONNECTED : 0u);
+        r.offset = base; r.count = emit ? total : 0u;
+        p.results[pi] = r;
+    }
+    epi_bar();
+    if (emit && S.base + total <= p.matches_cap) {
+        unsigned long long o = S.base + excl;
+        for (uint32_t a = lo; a < hi; ++a) {
+            const uint32_t b = m12[a];
+            if ((b != EACHAM_NONE) && (!p.cross_check || m21[b] == a)) {
+                eacham_match_t mt; mt.query = a; mt.train = b;
+                p.matches[o++] = mt;
+            }
+        }
+    }
+    epi_bar();
 }
 
 template <bool kOrb>
@@ -528,63 +615,7 @@ __global__ void __launch_bounds__(kThreadsTc, 1) tc_match_pairs_kernel(const Pai
             __threadfence_block();
             epi_bar();
 
-            // ---- gates, mutual filter, ordered compaction (main.cpp:111-146) ----
-            uint32_t c12 = 0, c21 = 0;
-            for (uint32_t i = et; i < N; i += kEpiThreads) c12 += m12[i] != EACHAM_NONE;
-            for (uint32_t j = et; j < M; j += kEpiThreads) c21 += m21[j] != EACHAM_NONE;
-            c12 = __reduce_add_sync(0xffffffffu, c12);
-            c21 = __reduce_add_sync(0xffffffffu, c21);
-            if (lane == 0) { S.red[e] = c12; S.red[kEpiWarps + e] = c21; }
-            epi_bar();
-            uint32_t n12 = 0, n21 = 0;
-#pragma unroll
-            for (int w = 0; w < kEpiWarps; ++w) { n12 += S.red[w]; n21 += S.red[kEpiWarps + w]; }
-            const bool gated = p.cross_check ? (n12 < p.min_dir || n21 < p.min_dir) : (n12 < p.min_dir);
-            const uint32_t per = (N + kEpiThreads - 1) / kEpiThreads;
-            const uint32_t lo = min(N, et * per), hi = min(N, lo + per);
-            uint32_t mine = 0;
-            if (!gated)
-                for (uint32_t a = lo; a < hi; ++a) {
-                    const uint32_t b = m12[a];
-                    mine += (b != EACHAM_NONE) && (!p.cross_check || m21[b] == a);
-                }
-            uint32_t incl = mine;
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                const uint32_t v = __shfl_up_sync(0xffffffffu, incl, o);
-                if (lane >= o) incl += v;
-            }
-            epi_bar();
-            if (lane == 31) S.red[e] = incl;
-            epi_bar();
-            uint32_t woff = 0, total = 0;
-#pragma unroll
-            for (int w = 0; w < kEpiWarps; ++w) { if (w < e) woff += S.red[w]; total += S.red[w]; }
-            const uint32_t excl = woff + incl - mine;
-            const bool connected = !gated && total > p.min_mutual;
-            const bool emit = !gated && (connected || p.emit_all) && total > 0;
-            if (et == 0) {
-                unsigned long long base = 0;
-                if (emit) base = atomicAdd(p.cursor, (unsigned long long)total);
-                S.base = base;
-                eacham_pair_result_t r;
-                r.n12 = n12; r.n21 = n21; r.n_mutual = gated ? 0u : total;
-                r.flags = (gated ? EACHAM_PAIR_GATED : 0u) | (connected ? EACHAM_PAIR_CONNECTED : 0u);
-                r.offset = base; r.count = emit ? total : 0u;
-                p.results[pi] = r;
-            }
-            epi_bar();
-            if (emit && S.base + total <= p.matches_cap) {
-                unsigned long long o = S.base + excl;
-                for (uint32_t a = lo; a < hi; ++a) {
-                    const uint32_t b = m12[a];
-                    if ((b != EACHAM_NONE) && (!p.cross_check || m21[b] == a)) {
-                        eacham_match_t mt; mt.query = a; mt.train = b;
-                        p.matches[o++] = mt;
-                    }
-                }
-            }
-            epi_bar();
+            gates_mutual_compact(S, p, pi, N, M, m12, m21, et, e, lane);
         }
     }
     tc::tc_fence_before();

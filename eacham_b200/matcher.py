@@ -68,9 +68,11 @@ class FeatureMatcherGpu:
         self.ratio = float(ratio)
         self.min_dir, self.min_mutual, self.cross_check = int(min_dir), int(min_mutual), bool(cross_check)
         self._lib = L.load()
-        if orb_engine not in ("popc", "tensor"):
-            raise ValueError("orb_engine must be 'tensor' (FP8 tensor-core engine, default) or 'popc' (XOR+POPC kernel)")
-        flags = (L.CFG_SIFT_EXACT_FP32 if sift_exact_fp32 else 0) | (L.CFG_ORB_POPC if orb_engine == "popc" else 0)
+        engines = {"tensor": 0, "popc": L.CFG_ORB_POPC, "tensor_v1": L.CFG_ORB_TC_V1, "tensor_alu": L.CFG_ORB_TC_ALU_SORT}
+        if orb_engine not in engines:
+            raise ValueError("orb_engine must be 'tensor' (FP8 tensor-core engine with F16 accumulators and packed epilogue, default), "
+                             "'popc' (XOR+POPC kernel), 'tensor_v1' (round-1 tensor kernel) or 'tensor_alu' (default engine, sort-2 on the ALU pipe)")
+        flags = (L.CFG_SIFT_EXACT_FP32 if sift_exact_fp32 else 0) | engines[orb_engine]
         self.orb_engine = orb_engine
         cfg = L.Config(device=device, max_images=0, match_buffer_entries=match_buffer_entries, flags=flags)
         h = ctypes.c_void_p()
@@ -227,7 +229,7 @@ class FeatureMatcherGpu:
         t = L.Timing()
         L.check(self._lib.eacham_gpu_last_timing(self._h, ctypes.byref(t)))
         return dict(upload_ms=t.upload_ms, pairs_h2d_ms=t.pairs_h2d_ms, kernel_ms=t.kernel_ms, d2h_ms=t.d2h_ms,
-                    kernel_launches=int(t.kernel_launches))
+                    kernel_launches=int(t.kernel_launches), prep_ms=t.prep_ms)
 
     def flush_l2(self, nbytes: int = 256 << 20) -> None:
         L.check(self._lib.eacham_gpu_flush_l2(self._h, nbytes))

@@ -1,15 +1,20 @@
 // FeatureMatcherGpu.h -- header-only C++ shim over the C ABI (include/eacham_gpu.h).
 //
-// Keeps the shape of the reference's matcher so apps/sfm/main.cpp compiles with the type swapped:
+// Keeps the shape of the reference's matcher so apps/sfm/main.cpp compiles with ONLY the type swapped:
 //   class FeatureMatcherFlann            /root/reference/modules/base/features/FeatureMatcherFlann.h:11-24
 //     ctor (const float inliersRatio)    :16
 //     MatchType Match(const cv::Mat&, const cv::Mat&)   :19,   MatchType = std::unordered_map<unsigned, unsigned>  :14
 //   IFeatureMatcher<T>::Match            /root/reference/modules/base/features/IFeatureMatcher.h:18-19
-// and adds MatchPairs(), which subsumes the pair loop + cross-check of /root/reference/apps/sfm/main.cpp:84-147.
+// `Match` is a plain (non-template, non-overloaded) member, so `&FeatureMatcherGpu::Match` has one type and the reference's
+//   std::async(std::launch::async, &FeatureMatcherFlann::Match, &matcher, d1, d2)      /root/reference/apps/sfm/main.cpp:107-108
+// binds unchanged. MatchPairs() subsumes the pair loop + cross-check of /root/reference/apps/sfm/main.cpp:84-147 and, given more
+// than one device, shards it over the GPUs of the box inside this process (eacham_gpu_multi_*).
 //
-// `Mat` is any type with the cv::Mat members used here: `rows`, `cols`, `type()`, `step` (convertible to size_t,
-// bytes per row) and `ptr<T>()`/`data`. With OpenCV present use cv::Mat directly; the unit test uses a stub.
-// Errors from the C ABI become std::runtime_error (the reference propagates cv::Exception the same way).
+// cv::Mat: with OpenCV on the include path the header pulls in <opencv2/core/mat.hpp> itself. Without OpenCV (this repo's test
+// image) define EACHAM_HAVE_CV_MAT after declaring a `cv::Mat` with the members used here -- `rows`, `cols`, `type()`, `step`
+// (convertible to size_t, bytes per row) and `data` -- which is what tests/cpp/shim_test.cpp does. MatchAny / MatchPairsAny are
+// the same calls for any other Mat-like type. Errors from the C ABI become std::runtime_error (the reference propagates
+// cv::Exception the same way).
 #pragma once
 
 #include <cstdint>
@@ -18,6 +23,13 @@
 #include <unordered_map>
 #include <utility>
 #include <vector>
+
+#if !defined(EACHAM_HAVE_CV_MAT) && defined(__has_include)
+#if __has_include(<opencv2/core/mat.hpp>)
+#include <opencv2/core/mat.hpp>
+#define EACHAM_HAVE_CV_MAT 1
+#endif
+#endif
 
 #include "../eacham_gpu.h"
 
@@ -41,8 +53,9 @@ public:
 
 public:
     // inliersRatio is stored and, like the reference (FeatureMatcherFlann.cpp:23 hard-codes 0.8), not used.
-    // flags: EACHAM_CFG_* bits (0 = defaults: tensor-core engine for ORB and SIFT; EACHAM_CFG_ORB_POPC selects the
-    // XOR+POPC kernel for ORB pairs, EACHAM_CFG_SIFT_EXACT_FP32 the all-FP32 SIFT kernels). Results do not depend on it.
+    // flags: EACHAM_CFG_* bits (0 = defaults: tensor-core engines for ORB and SIFT pairs). ORB results do not depend on the
+    // engine (bit-exact); SIFT results are bit-exact for integer-valued descriptors (what cv::SIFT emits) and agree within the
+    // epsilon stated in include/eacham_gpu.h for general floats.
     explicit FeatureMatcherGpu(const float inliersRatio, const int device = 0, const unsigned flags = 0)
         : inliersRatio{inliersRatio}
     {
@@ -53,14 +66,47 @@ public:
         eacham_gpu_default_opts(&opts);
     }
 
-    ~FeatureMatcherGpu() { eacham_gpu_destroy(handle); }
+    // Several GPUs of one box in this process: Match() runs on devices[0]; MatchPairs() uploads once, broadcasts the arena
+    // with NCCL and shards the pair list over all devices.
+    FeatureMatcherGpu(const float inliersRatio, const std::vector<int>& devices, const unsigned flags = 0)
+        : FeatureMatcherGpu(inliersRatio, devices.empty() ? 0 : devices[0], flags)
+    {
+        if (devices.size() > 1)
+        {
+            eacham_gpu_config cfg{};
+            cfg.flags = flags;
+            std::vector<int32_t> d(devices.begin(), devices.end());
+            const int rc = eacham_gpu_create_multi(d.data(), static_cast<uint32_t>(d.size()), &cfg, &multi);
+            if (rc != EACHAM_OK)
+            {
+                eacham_gpu_destroy(handle);
+                Check(rc);
+            }
+        }
+    }
+
+    ~FeatureMatcherGpu()
+    {
+        eacham_gpu_destroy_multi(multi);
+        eacham_gpu_destroy(handle);
+    }
     FeatureMatcherGpu(const FeatureMatcherGpu&) = delete;
     FeatureMatcherGpu& operator=(const FeatureMatcherGpu&) = delete;
 
 public:
-    // One direction, one pair; safe to call concurrently on one object (main.cpp:98-109 does).
+#ifdef EACHAM_HAVE_CV_MAT
+    // One direction, one pair: FeatureMatcherFlann::Match. Safe to call concurrently on one object (main.cpp:98-109 does).
+    MatchType Match(const cv::Mat& descriptor1, const cv::Mat& descriptor2) { return MatchAny(descriptor1, descriptor2); }
+
+    // Replaces main.cpp:84-147: descriptors[k] belongs to image id k; `pairs` holds each unordered pair once.
+    std::vector<PairMatches> MatchPairs(const std::vector<cv::Mat>& descriptors, const std::vector<std::pair<unsigned, unsigned>>& pairs)
+    {
+        return MatchPairsAny(descriptors, pairs);
+    }
+#endif
+
     template <typename Mat>
-    MatchType Match(const Mat& descriptor1, const Mat& descriptor2)
+    MatchType MatchAny(const Mat& descriptor1, const Mat& descriptor2)
     {
         const int kind = KindOf(descriptor1);
         if (KindOf(descriptor2) != kind) throw std::runtime_error("FeatureMatcherGpu::Match: descriptor types differ");
@@ -75,21 +121,38 @@ public:
         return matchesPair;
     }
 
-    // Replaces main.cpp:84-147: descriptors[k] belongs to image id k; `pairs` holds each unordered pair once.
     template <typename Mat>
-    std::vector<PairMatches> MatchPairs(const std::vector<Mat>& descriptors,
-                                        const std::vector<std::pair<unsigned, unsigned>>& pairs)
+    std::vector<PairMatches> MatchPairsAny(const std::vector<Mat>& descriptors,
+                                           const std::vector<std::pair<unsigned, unsigned>>& pairs)
     {
+        std::vector<eacham_pair_t> p(pairs.size());
+        for (size_t k = 0; k < pairs.size(); ++k) { p[k].first = pairs[k].first; p[k].second = pairs[k].second; }
+        std::vector<eacham_pair_result_t> res(pairs.size());
+        size_t used = 0;
+        const size_t guess = pairs.size() * 192 + 1024;
+        if (multi != nullptr)
+        {
+            Check(eacham_gpu_multi_clear(multi));
+            for (size_t k = 0; k < descriptors.size(); ++k)
+                Check(eacham_gpu_multi_set_descriptors(multi, static_cast<uint32_t>(k), KindOf(descriptors[k]), descriptors[k].data,
+                                                       static_cast<uint32_t>(descriptors[k].rows), Step(descriptors[k])));
+            Check(eacham_gpu_multi_commit(multi));
+            PinnedMatches buf(guess);       // page-locked: every device copies its shard at full PCIe rate
+            int rc = eacham_gpu_multi_match_pairs(multi, p.data(), p.size(), &opts, res.data(), buf.p, buf.n, &used);
+            if (rc == EACHAM_ERR_BUFFER_TOO_SMALL)
+            {
+                buf = PinnedMatches(used);
+                rc = eacham_gpu_multi_match_pairs(multi, p.data(), p.size(), &opts, res.data(), buf.p, buf.n, &used);
+            }
+            Check(rc);
+            return Unpack(pairs, res, buf.p);
+        }
         Check(eacham_gpu_clear(handle));
         for (size_t k = 0; k < descriptors.size(); ++k)
             Check(eacham_gpu_set_descriptors(handle, static_cast<uint32_t>(k), KindOf(descriptors[k]), descriptors[k].data,
                                              static_cast<uint32_t>(descriptors[k].rows), Step(descriptors[k])));
         Check(eacham_gpu_commit(handle));
-        std::vector<eacham_pair_t> p(pairs.size());
-        for (size_t k = 0; k < pairs.size(); ++k) { p[k].first = pairs[k].first; p[k].second = pairs[k].second; }
-        std::vector<eacham_pair_result_t> res(pairs.size());
-        std::vector<eacham_match_t> buf(pairs.size() * 192 + 1024);
-        size_t used = 0;
+        std::vector<eacham_match_t> buf(guess);
         int rc = eacham_gpu_match_pairs(handle, p.data(), p.size(), &opts, res.data(), buf.data(), buf.size(), &used);
         if (rc == EACHAM_ERR_BUFFER_TOO_SMALL)
         {
@@ -97,22 +160,7 @@ public:
             rc = eacham_gpu_fetch_results(handle, res.data(), res.size(), buf.data(), buf.size(), &used);
         }
         Check(rc);
-        std::vector<PairMatches> out(pairs.size());
-        for (size_t k = 0; k < pairs.size(); ++k)
-        {
-            PairMatches& m = out[k];
-            m.first = pairs[k].first; m.second = pairs[k].second;
-            m.n12 = res[k].n12; m.n21 = res[k].n21;
-            m.gated = (res[k].flags & EACHAM_PAIR_GATED) != 0;
-            m.connected = (res[k].flags & EACHAM_PAIR_CONNECTED) != 0;
-            for (uint64_t e = 0; e < res[k].count; ++e)
-            {
-                const eacham_match_t& mm = buf[res[k].offset + e];
-                m.bestMatches12[mm.query] = mm.train;
-                m.bestMatches21[mm.train] = mm.query;
-            }
-        }
-        return out;
+        return Unpack(pairs, res, buf.data());
     }
 
     // All unordered pairs of n images: one entry per two ordered pairs of main.cpp:84-92.
@@ -125,8 +173,50 @@ public:
     }
 
     eacham_match_opts& Options() { return opts; }
+    unsigned DeviceCount() const { return multi != nullptr ? eacham_gpu_multi_device_count(multi) : 1u; }
 
 private:
+    struct PinnedMatches
+    {
+        eacham_match_t* p = nullptr;
+        size_t n = 0;
+        explicit PinnedMatches(const size_t count) : p(static_cast<eacham_match_t*>(eacham_gpu_host_alloc((count ? count : 1) * sizeof(eacham_match_t)))), n(count)
+        {
+            if (p == nullptr) throw std::runtime_error(std::string("eacham_gpu: ") + eacham_gpu_last_error());
+        }
+        ~PinnedMatches() { eacham_gpu_host_free(p); }
+        PinnedMatches(const PinnedMatches&) = delete;
+        PinnedMatches& operator=(const PinnedMatches&) = delete;
+        PinnedMatches& operator=(PinnedMatches&& o) noexcept
+        {
+            if (this != &o) { eacham_gpu_host_free(p); p = o.p; n = o.n; o.p = nullptr; o.n = 0; }
+            return *this;
+        }
+    };
+
+    static std::vector<PairMatches> Unpack(const std::vector<std::pair<unsigned, unsigned>>& pairs,
+                                           const std::vector<eacham_pair_result_t>& res, const eacham_match_t* buf)
+    {
+        std::vector<PairMatches> out(pairs.size());
+        for (size_t k = 0; k < pairs.size(); ++k)
+        {
+            PairMatches& m = out[k];
+            m.first = pairs[k].first; m.second = pairs[k].second;
+            m.n12 = res[k].n12; m.n21 = res[k].n21;
+            m.gated = (res[k].flags & EACHAM_PAIR_GATED) != 0;
+            m.connected = (res[k].flags & EACHAM_PAIR_CONNECTED) != 0;
+            m.bestMatches12.reserve(res[k].count);
+            m.bestMatches21.reserve(res[k].count);
+            for (uint64_t e = 0; e < res[k].count; ++e)
+            {
+                const eacham_match_t& mm = buf[res[k].offset + e];
+                m.bestMatches12[mm.query] = mm.train;
+                m.bestMatches21[mm.train] = mm.query;
+            }
+        }
+        return out;
+    }
+
     template <typename Mat>
     static int KindOf(const Mat& m)
     {
@@ -147,6 +237,7 @@ private:
 private:
     float inliersRatio;
     eacham_gpu_handle* handle = nullptr;
+    eacham_gpu_multi* multi = nullptr;
     eacham_match_opts opts{};
 };
 

@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define EACHAM_GPU_ABI_VERSION 1
+#define EACHAM_GPU_ABI_VERSION 2
 
 #if defined(__GNUC__)
 #define EACHAM_API __attribute__((visibility("default")))
@@ -46,7 +46,8 @@ typedef enum eacham_status {
     EACHAM_ERR_BUFFER_TOO_SMALL = -5, /* caller buffer too small; the required count is reported back           */
     EACHAM_ERR_NOT_COMMITTED = -6,  /* match_pairs before commit, or an image id without descriptors            */
     EACHAM_ERR_TOO_LARGE = -7,      /* more descriptors per image than the kernels support (65535)              */
-    EACHAM_ERR_KIND_MISMATCH = -8   /* a pair mixes ORB and SIFT images                                          */
+    EACHAM_ERR_KIND_MISMATCH = -8,  /* a pair mixes ORB and SIFT images                                          */
+    EACHAM_ERR_NCCL = -9            /* multi-device: libnccl.so.2 missing or an NCCL call failed                  */
 } eacham_status;
 
 /* Descriptor kinds. ORB256: rows of 32 bytes (8 x int32, modules/base/tools/Tools3d.h:46-63), Hamming distance.
@@ -62,6 +63,9 @@ typedef struct eacham_gpu_handle eacham_gpu_handle;
 
 #define EACHAM_CFG_SIFT_EXACT_FP32 1u  /* SIFT pairs on the all-FP32 kernels (no tensor cores)                          */
 #define EACHAM_CFG_ORB_POPC 2u         /* ORB pairs on the XOR+POPC kernel instead of the default tensor-core engine (bits as FP8 0/1, exact) */
+#define EACHAM_CFG_ORB_TC_V1 4u        /* ORB pairs on the round-1 tensor-core kernel (F32 accumulators, 32-bit keys); for A/B measurements   */
+#define EACHAM_CFG_ORB_TC_ALU_SORT 8u  /* default ORB engine with its sort-2 steps on the ALU pipe instead of the FMA pipe; for A/B measurements */
+#define EACHAM_CFG_MULTI_PARALLEL_H2D 16u /* eacham_gpu_create_multi: one H2D copy per device instead of H2D + NCCL broadcast (no NCCL needed) */
 
 typedef struct eacham_gpu_config {
     int32_t device;               /* CUDA device ordinal                                                     */
@@ -110,7 +114,7 @@ typedef struct eacham_gpu_timing {
     float kernel_ms;    /* matching kernels only (inputs resident in HBM)                                     */
     float d2h_ms;       /* results + compacted matches D2H                                                    */
     uint32_t kernel_launches; /* kernels launched by the last match_pairs                                     */
-    uint32_t reserved;
+    float prep_ms;      /* tensor-core operand copy of the arena (bf16 / one e4m3 per bit), built once after a commit */
 } eacham_gpu_timing;
 
 EACHAM_API int eacham_gpu_abi_version(void);
@@ -165,6 +169,39 @@ EACHAM_API int eacham_gpu_fetch_results(eacham_gpu_handle* h, eacham_pair_result
 /* Device addresses of the last batch's outputs (results[n_pairs], matches[n_matches]); valid until the next
  * match_pairs call on this handle. Lets the plumbing layer gather shards over NVLink without a host round trip. */
 EACHAM_API int eacham_gpu_device_results(eacham_gpu_handle* h, void** results, void** matches, size_t* n_pairs, size_t* n_matches);
+
+/* ---- several devices of one box in ONE process (the reference is a single-process C++ app, apps/sfm/main.cpp) ----------
+ * The pair list shards with no data-path exchange: every device holds the whole arena, device g matches pairs
+ * g, g + n, g + 2n, ... and copies its own shard of the results into its slice of the caller's buffers over its own PCIe link.
+ * eacham_gpu_multi_commit = one H2D copy to devices[0] + ONE ncclBroadcast of the arena over NVLink (ncclCommInitAll, one stream
+ * per device; libnccl.so.2 is bound at run time). Results are exactly those of the single-device calls, in input order:
+ * buf holds device 0's matches, then device 1's, ...; res[k].offset indexes into buf. */
+typedef struct eacham_gpu_multi eacham_gpu_multi;
+
+typedef struct eacham_gpu_multi_timing {
+    float upload_ms;      /* wall clock: staging -> devices[0] (layout + H2D) inside the last commit                   */
+    float broadcast_ms;   /* wall clock: arena layout on the other devices + NCCL broadcast (or the per-device H2D)     */
+    float match_ms;       /* wall clock: pair sharding + all devices' kernels (the slowest device)                      */
+    float d2h_ms;         /* wall clock: all devices' result copies + re-interleaving                                   */
+    float kernel_ms_max;  /* CUDA events: matching kernels, max over devices                                            */
+    float prep_ms_max;    /* CUDA events: tensor-core operand copy, max over devices                                    */
+    uint32_t kernel_launches; /* summed over devices                                                                    */
+    uint32_t reserved;
+} eacham_gpu_multi_timing;
+
+EACHAM_API int eacham_gpu_create_multi(const int32_t* devices, uint32_t n_devices, const eacham_gpu_config* cfg, eacham_gpu_multi** out); /* cfg->device ignored */
+EACHAM_API void eacham_gpu_destroy_multi(eacham_gpu_multi* m);
+EACHAM_API uint32_t eacham_gpu_multi_device_count(eacham_gpu_multi* m);
+EACHAM_API int eacham_gpu_multi_set_descriptors(eacham_gpu_multi* m, uint32_t image_id, int kind, const void* data, uint32_t rows,
+                                                size_t row_stride_bytes);
+EACHAM_API int eacham_gpu_multi_clear(eacham_gpu_multi* m);
+EACHAM_API int eacham_gpu_multi_commit(eacham_gpu_multi* m);
+EACHAM_API int eacham_gpu_multi_match_pairs(eacham_gpu_multi* m, const eacham_pair_t* pairs, size_t n_pairs, const eacham_match_opts* opts,
+                                            eacham_pair_result_t* res, eacham_match_t* buf, size_t buf_cap, size_t* buf_used);
+EACHAM_API int eacham_gpu_multi_last_timing(eacham_gpu_multi* m, eacham_gpu_multi_timing* t);
+/* Page-locked host memory usable by every device (result buffers copied at full PCIe rate); NULL on failure. */
+EACHAM_API void* eacham_gpu_host_alloc(size_t bytes);
+EACHAM_API void eacham_gpu_host_free(void* p);
 
 EACHAM_API int eacham_gpu_last_timing(eacham_gpu_handle* h, eacham_gpu_timing* t);
 /* Write `bytes` of device memory (L2 flush between timed benchmark iterations). */

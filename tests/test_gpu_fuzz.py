@@ -41,7 +41,7 @@ def _check(m, descs, pairs, min_dir, min_mutual):
         assert np.array_equal(pm.matches.reshape(-1, 2), want["matches"].reshape(-1, 2)), (i, j)
 
 
-@pytest.mark.parametrize("engine", ["tensor", "popc"])
+@pytest.mark.parametrize("engine", ["tensor", "popc", "tensor_alu", "tensor_v1"])
 def test_fuzz_orb_ties(engine):
     import eacham_b200
     rng = np.random.default_rng(2026)

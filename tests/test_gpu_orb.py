@@ -12,7 +12,7 @@ pytestmark = pytest.mark.gpu
 NONE = 0xFFFFFFFF
 
 
-@pytest.fixture(scope="module", params=["tensor", "popc"])
+@pytest.fixture(scope="module", params=["tensor", "popc", "tensor_alu", "tensor_v1"])
 def matcher(request):
     """Every test below runs on both ORB engines: the tcgen05 FP8 engine (default) and the XOR+POPC kernel."""
     import eacham_b200
@@ -113,6 +113,19 @@ def test_options_ratio_and_gates(matcher):
         m.Upload([a, b])
         pm = m.MatchPairs([(0, 1)], emit_all=True)[0]
         assert pm.best12() == O.c_match(a, b)
+
+
+def test_ratio_above_one_keeps_opencv_tie_order(matcher):
+    """With ratio > 1 a query whose two best neighbours TIE passes the test, so OpenCV's tie order (lowest train index first)
+    becomes visible in the match set; the tensor engines hand such calls to the packed-key XOR+POPC kernels."""
+    import eacham_b200
+    rng = np.random.default_rng(17)
+    a = rng.integers(0, 4, (300, 32), dtype=np.uint8)          # low entropy: ties everywhere
+    b = rng.integers(0, 4, (280, 32), dtype=np.uint8)
+    b[200] = b[3]; b[150] = b[3]; a[10] = b[3]
+    with eacham_b200.FeatureMatcherGpu(0.8, ratio=1.25, min_dir=0, min_mutual=0, orb_engine=matcher.orb_engine) as m:
+        m.Upload([a, b])
+        _assert_pair_equal(m.MatchPairs([(0, 1)], emit_all=True)[0], O.c_match_pair(a, b, 1.25, 0, 0), "ratio 1.25")
 
 
 def test_strided_rows(matcher):

@@ -10,10 +10,10 @@ from test_gpu_orb import _assert_pair_equal
 pytestmark = pytest.mark.gpu
 
 
-@pytest.fixture(scope="module")
-def tmatcher():
+@pytest.fixture(scope="module", params=["tensor", "tensor_alu", "tensor_v1"])
+def tmatcher(request):
     import eacham_b200
-    m = eacham_b200.FeatureMatcherGpu(0.8, orb_engine="tensor")
+    m = eacham_b200.FeatureMatcherGpu(0.8, orb_engine=request.param)
     yield m
     m.close()
 

@@ -25,7 +25,7 @@ def test_library_builds_and_exports_header_symbols():
     for s in syms:
         assert hasattr(lib, s), f"{s} declared in include/eacham_gpu.h but not exported"
     assert sorted(_lib.SYMBOLS) == syms
-    assert _lib.load().eacham_gpu_abi_version() == 1
+    assert _lib.load().eacham_gpu_abi_version() == _lib.ABI_VERSION
 
 
 def test_struct_layouts_match_header():
@@ -34,6 +34,7 @@ def test_struct_layouts_match_header():
     assert np.dtype(L.PAIR_DTYPE).itemsize == 8
     assert np.dtype(L.RESULT_DTYPE).itemsize == 32
     assert ctypes.sizeof(L.MatchOpts) == 24 and ctypes.sizeof(L.Config) == 24 and ctypes.sizeof(L.Timing) == 24
+    assert ctypes.sizeof(L.MultiTiming) == 32
 
 
 def test_no_cpu_fallback_without_device():
@@ -46,6 +47,9 @@ def test_no_cpu_fallback_without_device():
     assert L.load().eacham_gpu_device_count() == 0
     with pytest.raises(L.EachamGpuError) as e:
         eacham_b200.FeatureMatcherGpu(0.8)
+    assert e.value.code == L.ERR_NO_DEVICE
+    with pytest.raises(L.EachamGpuError) as e:
+        eacham_b200.MultiGpuMatcher([0, 1])
     assert e.value.code == L.ERR_NO_DEVICE
 
 

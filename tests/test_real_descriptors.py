@@ -26,7 +26,7 @@ def test_c_oracle_on_real_descriptors():
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("engine", ["tensor", "popc"])
+@pytest.mark.parametrize("engine", ["tensor", "popc", "tensor_alu", "tensor_v1"])
 def test_gpu_on_real_descriptors(engine):
     import eacham_b200
     g = _cases()
