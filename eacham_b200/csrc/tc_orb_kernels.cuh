@@ -118,6 +118,8 @@ __device__ __forceinline__ void reduce16(const uint32_t (&v)[16], uint32_t& lo, 
     merge2(l[0], h[0], l[1], h[1], lo, hi);
 }
 
+__device__ __forceinline__ void quad_bar(int q) { asm volatile("bar.sync %0, 128;" ::"r"(2 + q) : "memory"); }
+
 __device__ __forceinline__ void tmem_ld16_pack(uint32_t taddr, uint32_t (&v)[16]) {
     asm volatile(
         "tcgen05.ld.sync.aligned.32x32b.x16.pack::16b.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
@@ -402,72 +404,82 @@ __global__ void __launch_bounds__(kThreads, 1) orb_tc_match_pairs_kernel(const P
                     if (tid == 0) EACHAM_TRACE(0, acc_it, 3);
                 }
                 // ---- rows of this block are complete: merge the four column parts, ratio test, recover the index ----
-                epi_bar();                                                  // every warp is done with its transpose buffer
-                if (cp > 0) {
+                // Only the four warps of a lane quadrant (they share the rows) meet: named barrier 2 + q, 128 threads. Their exchange
+                // area is the transpose buffer of the quadrant's first warp (all four are past their tile loops).
+                quad_bar(q);
+                uint4* rm = reinterpret_cast<uint4*>(S.u.xpose[q]);
 #pragma unroll
-                    for (int h = 0; h < 2; ++h) S.u.rowmerge[cp - 1][h * 128 + q * 32 + lane] = make_uint4(m0[h], m1[h], t0[h], 0u);
-                }
-                epi_bar();
-                if (cp == 0) {
+                for (int h = 0; h < 2; ++h) rm[(cp * 2 + h) * 32 + lane] = make_uint4(m0[h], m1[h], t0[h], 0u);
+                quad_bar(q);
+                {
+                    // two threads per row: both merge the parts, each checks 8 of the 16 candidate columns
+                    const int qt = cp * 32 + lane, rr = qt >> 1, half = qt & 1, h = rr >> 5, l = rr & 31;
+                    const uint32_t row = ab * kABlockRows + h * 128 + q * 32 + l;
+                    uint32_t best = 0xFFFFu, second = 0xFFFFu, wt = 0, wid = 0;
 #pragma unroll
-                    for (int h = 0; h < 2; ++h) {
-                        const uint32_t row = ab * kABlockRows + h * 128 + q * 32 + lane;
-                        uint32_t best = 0xFFFFu, second = 0xFFFFu, wt = 0, wid = 0;
+                    for (int c = 0; c < kColParts; ++c) {
+                        const uint4 o = rm[(c * 2 + h) * 32 + l];
 #pragma unroll
-                        for (int c = 0; c < kColParts; ++c) {
-                            uint4 o = make_uint4(m0[h], m1[h], t0[h], 0u);
-                            if (c > 0) o = S.u.rowmerge[c - 1][h * 128 + q * 32 + lane];
-#pragma unroll
-                            for (int par = 0; par < 2; ++par) {
-                                const uint32_t v = (o.x >> (16 * par)) & 0xFFFFu, w = (o.y >> (16 * par)) & 0xFFFFu;
-                                if (v < best) { second = min(second, best); best = v; wt = (o.z >> (16 * par)) & 0xFFFFu; wid = c * 2 + par; }
-                                else second = min(second, v);
-                                second = min(second, w);
-                            }
-                        }
-                        if (row < N) {
-                            uint32_t found = EACHAM_NONE, ham0 = 0;
-                            if (ratio_pass_f16(best, second, p.ratio, ham0)) {
-                                // the unique best lives in tile wt, column part wid / 2, column parity wid & 1: 16 candidates
-                                const uint32_t tile = (uint32_t)__half2int_rn(__ushort_as_half((unsigned short)wt));
-                                const uint32_t base = tile * 128 + (wid >> 1) * kColsPerWarp + (wid & 1);
-                                const uint4 a0 = __ldg(Aq + 2 * (size_t)row), a1 = __ldg(Aq + 2 * (size_t)row + 1);
-                                for (int i = 0; i < 16 && found == EACHAM_NONE; ++i) {
-                                    const uint32_t j = base + 2 * i;
-                                    if (j < M && hamming256(a0, a1, Bq + 2 * (size_t)j) == ham0) found = j;
-                                }
-                            }
-                            m12[row] = found;
+                        for (int par = 0; par < 2; ++par) {
+                            const uint32_t v = (o.x >> (16 * par)) & 0xFFFFu, w = (o.y >> (16 * par)) & 0xFFFFu;
+                            if (v < best) { second = min(second, best); best = v; wt = (o.z >> (16 * par)) & 0xFFFFu; wid = c * 2 + par; }
+                            else second = min(second, v);
+                            second = min(second, w);
                         }
                     }
+                    uint32_t found = EACHAM_NONE, ham0 = 0;
+                    if (row < N && ratio_pass_f16(best, second, p.ratio, ham0)) {
+                        // the unique best lives in tile wt, column part wid / 2, column parity wid & 1: 16 candidates
+                        const uint32_t tile = (uint32_t)__half2int_rn(__ushort_as_half((unsigned short)wt));
+                        const uint32_t base = tile * 128 + (wid >> 1) * kColsPerWarp + (wid & 1) + half * 16;
+                        const uint4 a0 = __ldg(Aq + 2 * (size_t)row), a1 = __ldg(Aq + 2 * (size_t)row + 1);
+#pragma unroll 4
+                        for (int i = 0; i < 8; ++i) {
+                            const uint32_t j = base + 2 * i;
+                            if (j < M && hamming256(a0, a1, Bq + 2 * (size_t)j) == ham0) found = min(found, j);
+                        }
+                    }
+                    found = min(found, __shfl_xor_sync(0xffffffffu, found, 1));
+                    if (half == 0 && row < N) m12[row] = found;
                 }
-                epi_bar();                                                  // rowmerge read: the transpose buffers are free again
+                quad_bar(q);                                                // exchange area read: the transpose buffer is free again
             }
 
             // ---- columns: merge the four quadrant states, ratio test, recover the row index among the 64 rows of (row block, quadrant) ----
+            epi_bar();
             __threadfence_block();
-            for (uint32_t j = et; j < M; j += kEpiThreads) {
+            for (uint32_t jb = e * 32; jb < M; jb += kEpiThreads) {
+                const uint32_t j = jb + lane;
                 uint32_t best = 0xFFFFu, second = 0xFFFFu, wab = 0, wq = 0;
+                if (j < M) {
 #pragma unroll
-                for (int qq = 0; qq < 4; ++qq) {
-                    const uint4 st = colq[(size_t)qq * colq_stride + (j >> 1)];
-                    const int sh = 16 * (j & 1);
-                    const uint32_t v = (st.x >> sh) & 0xFFFFu, w = (st.y >> sh) & 0xFFFFu;
-                    if (v < best) { second = min(second, best); best = v; wab = (st.z >> sh) & 0xFFFFu; wq = qq; }
-                    else second = min(second, v);
-                    second = min(second, w);
-                }
-                uint32_t found = EACHAM_NONE, ham0 = 0;
-                if (ratio_pass_f16(best, second, p.ratio, ham0)) {
-                    // the unique best lives in row block wab, lane quadrant wq: 64 candidate rows
-                    const uint32_t base = (uint32_t)__half2int_rn(__ushort_as_half((unsigned short)wab)) * kABlockRows + wq * 32;
-                    const uint4 b0 = __ldg(Bq + 2 * (size_t)j), b1 = __ldg(Bq + 2 * (size_t)j + 1);
-                    for (int i = 0; i < 64 && found == EACHAM_NONE; ++i) {
-                        const uint32_t r = base + (i >> 5) * 128 + (i & 31);
-                        if (r < N && hamming256(b0, b1, Aq + 2 * (size_t)r) == ham0) found = r;
+                    for (int qq = 0; qq < 4; ++qq) {
+                        const uint4 st = colq[(size_t)qq * colq_stride + (j >> 1)];
+                        const int sh = 16 * (j & 1);
+                        const uint32_t v = (st.x >> sh) & 0xFFFFu, w = (st.y >> sh) & 0xFFFFu;
+                        if (v < best) { second = min(second, best); best = v; wab = (st.z >> sh) & 0xFFFFu; wq = qq; }
+                        else second = min(second, v);
+                        second = min(second, w);
                     }
                 }
-                m21[j] = found;
+                uint32_t ham0 = 0;
+                const bool pass = j < M && ratio_pass_f16(best, second, p.ratio, ham0);
+                // the unique best of a passing column lives in row block wab, lane quadrant wq: 64 candidate rows, checked by the
+                // whole warp at once (two per lane)
+                const uint32_t base = (uint32_t)__half2int_rn(__ushort_as_half((unsigned short)wab)) * kABlockRows + wq * 32;
+                uint32_t found = EACHAM_NONE;
+                for (uint32_t mask = __ballot_sync(0xffffffffu, pass); mask; mask &= mask - 1) {
+                    const int src = __ffs(mask) - 1;
+                    const uint32_t jj = __shfl_sync(0xffffffffu, j, src), bb = __shfl_sync(0xffffffffu, base, src), hh = __shfl_sync(0xffffffffu, ham0, src);
+                    const uint4 b0 = __ldg(Bq + 2 * (size_t)jj), b1 = __ldg(Bq + 2 * (size_t)jj + 1);
+                    const uint32_t r0 = bb + lane, r1 = bb + 128 + lane;
+                    const bool e0 = r0 < N && hamming256(b0, b1, Aq + 2 * (size_t)r0) == hh;
+                    const bool e1 = r1 < N && hamming256(b0, b1, Aq + 2 * (size_t)r1) == hh;
+                    const uint32_t k0 = __ballot_sync(0xffffffffu, e0), k1 = __ballot_sync(0xffffffffu, e1);
+                    const uint32_t r = k0 ? bb + (__ffs(k0) - 1) : (k1 ? bb + 128 + (__ffs(k1) - 1) : EACHAM_NONE);
+                    if (lane == src) found = r;
+                }
+                if (j < M) m21[j] = found;
             }
             __threadfence_block();
             epi_bar();
