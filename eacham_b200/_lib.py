@@ -29,7 +29,8 @@ class MatchOpts(ctypes.Structure):
 
 class Timing(ctypes.Structure):
     _fields_ = [("upload_ms", ctypes.c_float), ("pairs_h2d_ms", ctypes.c_float), ("kernel_ms", ctypes.c_float),
-                ("d2h_ms", ctypes.c_float), ("kernel_launches", ctypes.c_uint32), ("prep_ms", ctypes.c_float)]
+                ("d2h_ms", ctypes.c_float), ("kernel_launches", ctypes.c_uint32), ("prep_ms", ctypes.c_float),
+                ("exact_fallbacks", ctypes.c_uint32), ("reserved", ctypes.c_uint32)]
 
 
 class MultiTiming(ctypes.Structure):
@@ -52,7 +53,7 @@ SYMBOLS = [
     "eacham_gpu_flush_l2",
     "eacham_gpu_create_multi", "eacham_gpu_destroy_multi", "eacham_gpu_multi_device_count", "eacham_gpu_multi_set_descriptors",
     "eacham_gpu_multi_clear", "eacham_gpu_multi_commit", "eacham_gpu_multi_match_pairs", "eacham_gpu_multi_last_timing",
-    "eacham_gpu_host_alloc", "eacham_gpu_host_free",
+    "eacham_gpu_host_alloc", "eacham_gpu_host_free", "eacham_gpu_debug_pair_knn2",
 ]
 
 _lib = None
@@ -97,6 +98,7 @@ def load() -> ctypes.CDLL:
     lib.eacham_gpu_device_results.argtypes = [vp, P(vp), P(vp), P(sz), P(sz)]
     lib.eacham_gpu_last_timing.argtypes = [vp, P(Timing)]
     lib.eacham_gpu_flush_l2.argtypes = [vp, sz]
+    lib.eacham_gpu_debug_pair_knn2.argtypes = [vp, u32, u32, P(MatchOpts), vp, vp, vp, vp]
     lib.eacham_gpu_create_multi.argtypes = [P(ctypes.c_int32), u32, P(Config), P(vp)]
     lib.eacham_gpu_destroy_multi.argtypes = [vp]
     lib.eacham_gpu_destroy_multi.restype = None

@@ -104,6 +104,11 @@ struct eacham_gpu_handle {
     uint32_t cfg_flags = 0;
 
     DevBuf<eacham_pair_t> d_pairs;
+    DevBuf<uint32_t> d_order;
+    DevBuf<int32_t> d_dbg_idx;                // debug kNN of one pair: [rows12 * 2 | rows21 * 2]
+    DevBuf<float> d_dbg_dist;
+    bool dbg_on = false;
+    std::vector<uint32_t> order_host, order_count;
     DevBuf<eacham_pair_result_t> d_results;
     DevBuf<eacham_match_t> d_matches;
     DevBuf<uint32_t> d_counter;               // [0] work counter
@@ -240,7 +245,7 @@ void eacham_gpu_destroy(eacham_gpu_handle* h) {
         DeviceGuard g(h->device);
         if (h->stream) cudaStreamSynchronize(h->stream);
         h->tc_arena.release(); h->d_images_tc.release(); h->d_block_start.release(); h->tc_scratch.release();
-        h->arena.release(); h->d_images.release(); h->d_pairs.release(); h->d_results.release(); h->d_matches.release();
+        h->arena.release(); h->d_images.release(); h->d_pairs.release(); h->d_order.release(); h->d_dbg_idx.release(); h->d_dbg_dist.release(); h->d_results.release(); h->d_matches.release();
         h->d_counter.release(); h->d_cursor.release(); h->d_q.release(); h->d_t.release(); h->d_partial.release();
         h->d_idx.release(); h->d_dist.release(); h->d_match.release(); h->d_match2.release(); h->d_flush.release();
         if (h->staging) cudaFreeHost(h->staging);
@@ -503,6 +508,7 @@ int prepare_tc(eacham_gpu_handle* h) {
         const ImageHost& im = h->images[i];
         table[i].offset = im.offset; table[i].tc_offset = h->tc_offsets[i];
         table[i].rows = im.present ? im.rows : 0; table[i].kind = im.present ? (uint32_t)im.kind : 0xffffffffu;
+        table[i].max_norm_bits = 0u; table[i].bf16_exact = 1u;            // refined by the prep kernel (F32X128)
         block_start[i] = blocks;
         const bool has_tc = im.present && im.rows > 0 && (im.kind == EACHAM_KIND_F32X128 || !(h->cfg_flags & EACHAM_CFG_ORB_POPC));
         if (has_tc) blocks += (im.rows + 127) / 128;
@@ -555,7 +561,25 @@ int launch_pairs(eacham_gpu_handle* h, const eacham_pair_t* pairs, size_t n_pair
 
     int rc;
     if ((rc = h->d_pairs.ensure(n_pairs))) return rc;
+    if ((rc = h->d_order.ensure(n_pairs))) return rc;
     if ((rc = h->d_results.ensure(n_pairs))) return rc;
+    // Processing order: the image x image grid is cut into kBlock x kBlock blocks and the pairs of one block are handed out together
+    // (counting sort by block, stable), so that the ~148 pairs in flight share a few dozen images that stay L2-resident instead of
+    // streaming 148 different second images from HBM. Results are written at the pair's input index.
+    {
+        constexpr uint32_t kBlock = 16;
+        const uint32_t nb = (uint32_t)((h->images.size() + kBlock - 1) / kBlock);
+        const bool small = (size_t)nb * nb > 4 * n_pairs + 1024;          // sparse lists over huge id ranges: keep the input order
+        h->order_host.resize(n_pairs);
+        if (small) {
+            for (size_t i = 0; i < n_pairs; ++i) h->order_host[i] = (uint32_t)i;
+        } else {
+            h->order_count.assign((size_t)nb * nb + 1, 0u);
+            for (size_t i = 0; i < n_pairs; ++i) ++h->order_count[(size_t)(pairs[i].first / kBlock) * nb + pairs[i].second / kBlock + 1];
+            for (size_t b = 1; b < h->order_count.size(); ++b) h->order_count[b] += h->order_count[b - 1];
+            for (size_t i = 0; i < n_pairs; ++i) h->order_host[h->order_count[(size_t)(pairs[i].first / kBlock) * nb + pairs[i].second / kBlock]++] = (uint32_t)i;
+        }
+    }
     size_t want_entries = h->cfg_match_entries ? (size_t)h->cfg_match_entries
                                                : std::max((size_t)1 << 20, n_pairs * (size_t)192);
     if (h->d_matches.cap < want_entries && (rc = h->d_matches.ensure(want_entries))) return rc;
@@ -567,16 +591,17 @@ int launch_pairs(eacham_gpu_handle* h, const eacham_pair_t* pairs, size_t n_pair
     if (use_tc && (rc = prepare_tc(h))) return rc;
     CUDA_TRY(cudaEventRecord(h->ev[2], h->stream));
     CUDA_TRY(cudaMemcpyAsync(h->d_pairs.p, pairs, n_pairs * sizeof(eacham_pair_t), cudaMemcpyHostToDevice, h->stream));
+    CUDA_TRY(cudaMemcpyAsync(h->d_order.p, h->order_host.data(), n_pairs * sizeof(uint32_t), cudaMemcpyHostToDevice, h->stream));
     CUDA_TRY(cudaEventRecord(h->ev[3], h->stream));
 
     for (int attempt = 0; attempt < 2; ++attempt) {
-        CUDA_TRY(cudaMemsetAsync(h->d_counter.p, 0, sizeof(uint32_t), h->stream));
+        CUDA_TRY(cudaMemsetAsync(h->d_counter.p, 0, 2 * sizeof(uint32_t), h->stream));       // [0] pair queue, [1] exact-scan fallbacks
         CUDA_TRY(cudaMemsetAsync(h->d_cursor.p, 0, sizeof(unsigned long long), h->stream));
         CUDA_TRY(cudaEventRecord(h->ev[4], h->stream));
         if (kind == EACHAM_KIND_ORB256 && !use_tc && max_first <= orb::kMaxRowsFused && max_second <= orb::kMaxRowsFused) {
             orb::PairParams p;
             p.arena = h->arena.p; p.images = h->d_images.p; p.pairs = h->d_pairs.p; p.n_pairs = (uint32_t)n_pairs;
-            p.work_counter = h->d_counter.p;
+            p.work_counter = h->d_counter.p; p.order = h->d_order.p;
             p.ratio = o.ratio; p.min_dir = o.min_dir; p.min_mutual = o.min_mutual; p.cross_check = o.cross_check; p.emit_all = o.emit_all;
             p.results = h->d_results.p; p.matches = h->d_matches.p; p.matches_cap = h->d_matches.cap; p.cursor = h->d_cursor.p;
             p.smem_cols = (uint32_t)align_up(std::max(max_second, 4u), 4);
@@ -599,7 +624,12 @@ int launch_pairs(eacham_gpu_handle* h, const eacham_pair_t* pairs, size_t n_pair
             const unsigned grid = (unsigned)std::min<size_t>(n_pairs, (size_t)h->sm_count);
             if ((rc = h->tc_scratch.ensure(tcm::tc_scratch_bytes_per_cta(p.rows_cap, p.cols_cap) * grid))) return rc;
             p.scratch = h->tc_scratch.p;
-            p.work_counter = h->d_counter.p;
+            p.work_counter = h->d_counter.p; p.order = h->d_order.p; p.exact_fallbacks = h->d_counter.p + 1;
+            p.dbg_idx12 = p.dbg_idx21 = nullptr; p.dbg_dist12 = p.dbg_dist21 = nullptr;
+            if (h->dbg_on && n_pairs == 1) {
+                p.dbg_idx12 = h->d_dbg_idx.p; p.dbg_dist12 = h->d_dbg_dist.p;
+                p.dbg_idx21 = h->d_dbg_idx.p + 2 * (size_t)max_first; p.dbg_dist21 = h->d_dbg_dist.p + 2 * (size_t)max_first;
+            }
             const size_t smem = sizeof(tcm::SmemTc) + 128;
             if (kind == EACHAM_KIND_ORB256 && !(h->cfg_flags & EACHAM_CFG_ORB_TC_V1)) {
                 // default: F16 accumulators, packed epilogue (tc_orb_kernels.cuh)
@@ -642,8 +672,11 @@ int launch_pairs(eacham_gpu_handle* h, const eacham_pair_t* pairs, size_t n_pair
         }
         CUDA_TRY(cudaEventRecord(h->ev[5], h->stream));
         unsigned long long used = 0;
+        uint32_t counters[2] = {0, 0};
         CUDA_TRY(cudaMemcpyAsync(&used, h->d_cursor.p, sizeof(used), cudaMemcpyDeviceToHost, h->stream));
+        CUDA_TRY(cudaMemcpyAsync(counters, h->d_counter.p, sizeof(counters), cudaMemcpyDeviceToHost, h->stream));
         CUDA_TRY(cudaStreamSynchronize(h->stream));
+        h->timing.exact_fallbacks = counters[1];
         if (used <= h->d_matches.cap) { h->last_total = used; break; }
         if (attempt == 1) return fail(EACHAM_ERR_OUT_OF_MEMORY, "match buffer overflow persisted after regrow");
         if ((rc = h->d_matches.ensure((size_t)used + 1024))) return rc;   // deterministic need: rerun once
@@ -712,5 +745,31 @@ int eacham_gpu_match_pairs(eacham_gpu_handle* h, const eacham_pair_t* pairs, siz
 }
 
 }  // extern "C"
+
+extern "C" int eacham_gpu_debug_pair_knn2(eacham_gpu_handle* h, uint32_t first, uint32_t second, const eacham_match_opts* opts, int32_t* idx12,
+                                          float* dist12, int32_t* idx21, float* dist21) {
+    if (!h || !idx12 || !dist12 || !idx21 || !dist21) return fail(EACHAM_ERR_INVALID_ARG, "null argument");
+    std::lock_guard<std::mutex> lk(h->mu);
+    DeviceGuard g(h->device);
+    if (first >= h->images.size() || second >= h->images.size() || !h->images[first].present || !h->images[second].present)
+        return fail(EACHAM_ERR_NOT_COMMITTED, "pair (%u, %u) names an image without descriptors", first, second);
+    if (h->images[first].kind != EACHAM_KIND_F32X128 || (h->cfg_flags & EACHAM_CFG_SIFT_EXACT_FP32))
+        return fail(EACHAM_ERR_INVALID_ARG, "the debug kNN view exists for F32X128 pairs on the tensor-core engine only");
+    const size_t n1 = h->images[first].rows, n2 = h->images[second].rows;
+    int rc;
+    if ((rc = h->d_dbg_idx.ensure(2 * (n1 + n2) + 4)) || (rc = h->d_dbg_dist.ensure(2 * (n1 + n2) + 4))) return rc;
+    CUDA_TRY(cudaMemsetAsync(h->d_dbg_idx.p, 0xFF, (2 * (n1 + n2) + 4) * sizeof(int32_t), h->stream));
+    eacham_pair_t pr; pr.first = first; pr.second = second;
+    h->dbg_on = true;
+    rc = launch_pairs(h, &pr, 1, opts);
+    h->dbg_on = false;
+    if (rc) return rc;
+    CUDA_TRY(cudaMemcpyAsync(idx12, h->d_dbg_idx.p, 2 * n1 * sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(cudaMemcpyAsync(dist12, h->d_dbg_dist.p, 2 * n1 * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(cudaMemcpyAsync(idx21, h->d_dbg_idx.p + 2 * n1, 2 * n2 * sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(cudaMemcpyAsync(dist21, h->d_dbg_dist.p + 2 * n1, 2 * n2 * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(cudaStreamSynchronize(h->stream));
+    return EACHAM_OK;
+}
 
 #include "multi.cuh"

@@ -52,6 +52,7 @@ struct PairParams {
     const eacham_pair_t* pairs;
     uint32_t n_pairs;
     uint32_t* work_counter;
+    const uint32_t* order;   // work item k is pair order[k] (L2-blocked processing order; results stay in input order)
     double ratio;
     uint32_t min_dir, min_mutual, cross_check, emit_all;
     eacham_pair_result_t* results;
@@ -191,10 +192,10 @@ __global__ void __launch_bounds__(kThreads, 1) orb_match_pairs_kernel(const Pair
     uint32_t seq = 0;   // chunks consumed so far by this CTA: buffer = seq & 1, parity = (seq >> 1) & 1
 
     for (;;) {
-        if (tid == 0) s_u32[0] = atomicAdd(p.work_counter, 1u);
+        if (tid == 0) { const uint32_t wk = atomicAdd(p.work_counter, 1u); s_u32[0] = wk < p.n_pairs ? p.order[wk] : 0xFFFFFFFFu; }
         __syncthreads();
         const uint32_t pi = s_u32[0];
-        if (pi >= p.n_pairs) break;
+        if (pi == 0xFFFFFFFFu) break;
         const eacham_pair_t pr = p.pairs[pi];
         const ImageDesc A = p.images[pr.first], B = p.images[pr.second];
         const uint32_t N = A.rows, M = B.rows;

@@ -7,7 +7,13 @@
 //   gates + mutual filter           /root/reference/apps/sfm/main.cpp:111-146
 // Candidate scoring runs as a bf16 GEMM with fp32 accumulation in tensor memory; the two best candidates per row and
 // per column are then re-ranked with exact FP32 arithmetic (sqrtf(sum (a-b)^2), float accumulator) so that the
-// distances the ratio test sees are the reference's. See DESIGN.md "SIFT kernel".
+// distances the ratio test sees are the reference's.
+// Exactness of the MATCH SET (see rerank_ratio_checked): the scorer's candidates minimise an approximate key whose distance
+// from the true |a-b|^2/2 is bounded (bf16 rounding of the inputs -- zero for integer-valued rows, which is what cv::SIFT emits --
+// plus the 2^-15 relative key truncation). From that bound every query gets an interval for the reference's ratio; only when
+// the interval straddles the threshold (or the best itself could be a non-candidate) is the answer not yet certain, and those
+// queries are re-done by an exact FP32 scan over ALL train rows. So the match sets equal the exact matcher's for any float
+// input; there is no epsilon left in the result, only in how many queries take the slow path. See DESIGN.md "SIFT kernel".
 #pragma once
 #include <cstdint>
 #include <cuda_bf16.h>
@@ -30,7 +36,8 @@ __device__ __forceinline__ void split3(float x, __nv_bfloat16& hi, __nv_bfloat16
 
 // fp32 rows [rows][128] -> pre-tiled bf16 blocks (tc_common.cuh layout). One warp per row; grid covers
 // n_blocks * 128 rows (rows >= `rows` are padding: zero data, norm 1e30 so they never win a minimum).
-__device__ __forceinline__ void sift_prep_row(const float* __restrict__ src, uint32_t rows, uint8_t* __restrict__ dst, uint32_t row, int lane) {
+__device__ __forceinline__ void sift_prep_row(const float* __restrict__ src, uint32_t rows, uint8_t* __restrict__ dst, uint32_t row, int lane,
+                                              uint32_t* max_norm_bits = nullptr, uint32_t* bf16_exact = nullptr) {
     uint8_t* blk = dst + (size_t)(row / tc::kBlockRows) * tc::kBlockBytes;
     const uint32_t r = row % tc::kBlockRows;
     float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -41,6 +48,13 @@ __device__ __forceinline__ void sift_prep_row(const float* __restrict__ src, uin
     float n = f0 * f0 + f1 * f1 + f2 * f2 + f3 * f3;       // norm of the ROUNDED row: D = |a-b|^2/2 stays consistent
 #pragma unroll
     for (int o = 16; o >= 1; o >>= 1) n += __shfl_xor_sync(0xffffffffu, n, o);
+    if (max_norm_bits != nullptr && row < rows) {           // per-image facts the matcher's error bound needs
+        const bool exact = __all_sync(0xffffffffu, f0 == v.x && f1 == v.y && f2 == v.z && f3 == v.w);
+        if (lane == 0) {
+            atomicMax(max_norm_bits, __float_as_uint(sqrtf(n)));          // n >= 0: the bit pattern orders like the value
+            if (!exact) atomicAnd(bf16_exact, 0u);
+        }
+    }
     // lane l holds dims 4l..4l+3 -> chunk l/2, bytes (l&1)*8 .. +8 of the row's 16-byte slot
     __nv_bfloat162 p0 = __halves2bfloat162(b0, b1), p1 = __halves2bfloat162(b2, b3);
     uint2 packed;
@@ -121,12 +135,14 @@ struct ImageDescTc {
     unsigned long long tc_offset;   // pre-tiled blocks in the tc arena
     uint32_t rows;
     uint32_t kind;
+    uint32_t max_norm_bits;         // F32X128: float bits of the largest row norm (of the bf16-rounded rows); filled by the prep kernel
+    uint32_t bf16_exact;            // F32X128: 1 if every value is exactly representable in bf16 (integer-valued SIFT): scoring is exact
 };
 
 // The whole image table in ONE launch: CTA b handles 8 rows of 128-row block b / 16; block_start[i] = first block of image i
 // (prefix sums, n_images + 1 entries; images without a tensor-core copy have an empty range).
 __global__ void __launch_bounds__(256) tc_prep_all_kernel(const uint8_t* __restrict__ arena, uint8_t* __restrict__ tc_arena,
-                                                          const ImageDescTc* __restrict__ images, const uint32_t* __restrict__ block_start,
+                                                          ImageDescTc* images, const uint32_t* __restrict__ block_start,
                                                           uint32_t n_images) {
     const uint32_t blk = blockIdx.x / 16;
     uint32_t lo = 0, hi = n_images;                     // last image with block_start[i] <= blk
@@ -137,7 +153,8 @@ __global__ void __launch_bounds__(256) tc_prep_all_kernel(const uint8_t* __restr
     const ImageDescTc im = images[lo];
     const uint32_t row = (blk - __ldg(block_start + lo)) * tc::kBlockRows + (blockIdx.x % 16) * 8 + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
-    if (im.kind == EACHAM_KIND_F32X128) sift_prep_row(reinterpret_cast<const float*>(arena + im.offset), im.rows, tc_arena + im.tc_offset, row, lane);
+    if (im.kind == EACHAM_KIND_F32X128) sift_prep_row(reinterpret_cast<const float*>(arena + im.offset), im.rows, tc_arena + im.tc_offset, row, lane,
+                                                      &images[lo].max_norm_bits, &images[lo].bf16_exact);
     else orb_tc_prep_row(arena + im.offset, im.rows, tc_arena + im.tc_offset, row, lane);
 }
 
@@ -174,6 +191,10 @@ struct PairParamsTc {
     uint8_t* scratch;               // per CTA: colstate (16 B x cols_cap) + m12 (4 B x rows_cap) + m21 (4 B x cols_cap)
     uint32_t rows_cap, cols_cap;    // multiples of 128
     uint32_t* work_counter;         // dynamic pair queue (zeroed by the host before the launch)
+    const uint32_t* order;          // processing order: work item k is pair order[k] (L2-blocked by the host); results stay in input order
+    uint32_t* exact_fallbacks;      // F32X128: number of queries re-done by the exact scan (statistics)
+    // debug (single-pair calls, F32X128): the kNN(k=2) the ratio test saw, per row of `first` / of `second`: idx[n][2], dist[n][2]
+    int32_t* dbg_idx12; float* dbg_dist12; int32_t* dbg_idx21; float* dbg_dist21;
 };
 
 constexpr int kEpiWarps = 16;          // 4 per TMEM lane quadrant, 32 columns of every tile each
@@ -224,16 +245,77 @@ __device__ __forceinline__ float exact_l2(const float4 a4, const float* __restri
     return __fsqrt_rn(s);
 }
 
-// re-rank two candidates of one query row exactly, apply the ratio test; returns the train index or EACHAM_NONE
-__device__ __forceinline__ uint32_t rerank_ratio(const float* __restrict__ qrow, const float* __restrict__ tbase, uint32_t j0,
-                                                 uint32_t j1, uint32_t n_train, double ratio, int lane) {
+// kNN(k=2) of one query row by an exact scan over ALL train rows (OpenCV order: ascending distance, ties to the lower index),
+// warp-cooperative with the same arithmetic as the re-rank (exact_l2). The slow path of rerank_ratio_checked.
+__device__ __forceinline__ void exact_scan_top2(const float4 a4, const float* __restrict__ tbase, uint32_t n_train, int lane,
+                                                float& d0, float& d1, uint32_t& j0, uint32_t& j1) {
+    d0 = d1 = __int_as_float(0x7f800000);
+    j0 = j1 = EACHAM_NONE;
+    uint32_t j = 0;
+    for (; j + 2 <= n_train; j += 2) {                   // two train rows per step: independent loads
+        const float da = exact_l2(a4, tbase + (size_t)j * 128, lane);
+        const float db = exact_l2(a4, tbase + (size_t)(j + 1) * 128, lane);
+        if (da < d1) { if (da < d0) { d1 = d0; j1 = j0; d0 = da; j0 = j; } else { d1 = da; j1 = j; } }
+        if (db < d1) { if (db < d0) { d1 = d0; j1 = j0; d0 = db; j0 = j + 1; } else { d1 = db; j1 = j + 1; } }
+    }
+    if (j < n_train) {
+        const float da = exact_l2(a4, tbase + (size_t)j * 128, lane);
+        if (da < d1) { if (da < d0) { d1 = d0; j1 = j0; d0 = da; j0 = j; } else { d1 = da; j1 = j; } }
+    }
+}
+
+// Re-rank the scorer's two candidates of one query row exactly and apply the ratio test (FeatureMatcherFlann.cpp:21-27); returns
+// the train index or EACHAM_NONE. All lanes of the warp take part and return the same value.
+//
+// Certainty check. Let s(.) be the scorer's key order and D = |a-b|^2 / 2. The candidates j0, j1 minimise s, and
+// |s(c) - D(c)| <= E for every train row c, so every NON-candidate c has D(c) >= D(j1) - 2E, i.e. d(c)^2 >= X := d1^2 - 4E.
+//   E = E_round + E_trunc + E_acc
+//   E_round = delta (2 d1 + delta) / 2,  delta = 2^-9 (|a| + max_c |b_c|)   bf16 rounding of both operands (0 if both images are bf16-exact)
+//   E_trunc = 2^-15 D(j1)                                                  keys keep 16 mantissa bits of D
+//   E_acc   = 2^-16 (|a|^2 + max|b|^2) / 2                                  fp32 accumulation of inexact products (0 if bf16-exact: integer sums < 2^24)
+// The reference's ratio is d0/d1 if no non-candidate enters its top two, and lies in [d0/d1, d0/sqrt(X)] if one becomes second; a
+// non-candidate can only be the BEST if X < d0^2. Hence:
+//   d0/sqrt(X) < ratio                      -> match j0 for certain
+//   d0/d1 >= ratio and sqrt(X) >= ratio d0  -> no match for certain
+//   otherwise                               -> exact scan over all train rows (counted in *fallbacks)
+__device__ __forceinline__ uint32_t rerank_ratio_checked(const float* __restrict__ qrow, const float* __restrict__ tbase, uint32_t j0, uint32_t j1,
+                                                         uint32_t n_train, double ratio, int lane, bool exact_inputs, float other_max_norm,
+                                                         uint32_t* fallbacks, int32_t* dbg_idx, float* dbg_dist) {
     const float4 a4 = __ldg(reinterpret_cast<const float4*>(qrow) + lane);
     const bool v0 = j0 < n_train, v1 = j1 < n_train;
     float d0 = v0 ? exact_l2(a4, tbase + (size_t)j0 * 128, lane) : __int_as_float(0x7f800000);
     float d1 = v1 ? exact_l2(a4, tbase + (size_t)j1 * 128, lane) : __int_as_float(0x7f800000);
     if (d1 < d0 || (d1 == d0 && j1 < j0)) { const float t = d0; d0 = d1; d1 = t; const uint32_t u = j0; j0 = j1; j1 = u; }
-    if (!(v0 && v1)) return EACHAM_NONE;                 // fewer than two neighbours: reference is UB, rejected
-    return ((double)__fdiv_rn(d0, d1) < ratio) ? j0 : EACHAM_NONE;
+    uint32_t result = EACHAM_NONE;
+    if (v0 && v1) {                                      // fewer than two neighbours: the reference is UB, rejected
+        float E = 0.5f * d1 * d1 * 3.0517578125e-5f;                                   // E_trunc
+        if (!exact_inputs) {
+            float n = a4.x * a4.x + a4.y * a4.y + a4.z * a4.z + a4.w * a4.w;
+#pragma unroll
+            for (int o = 16; o >= 1; o >>= 1) n += __shfl_xor_sync(0xffffffffu, n, o);
+            const float na = sqrtf(n) * 1.004f, nb = other_max_norm * 1.004f;
+            const float delta = 1.953125e-3f * (na + nb) * 1.01f;
+            E += 0.5f * delta * (2.f * d1 + delta) + 1.52587890625e-5f * 0.5f * (na * na + nb * nb);
+        }
+        const float X = d1 * d1 - 4.f * E * 1.001f;
+        const bool lo_pass = (double)__fdiv_rn(d0, d1) < ratio;
+        bool certain = false;
+        if (X > 0.f) {
+            const float sx = sqrtf(X) * 0.999999f;
+            if ((double)(d0 / sx * 1.000001f) < ratio) { certain = true; result = j0; }
+            else if (!lo_pass && (double)sx >= ratio * (double)d0 * 1.000001) certain = true;
+        }
+        if (!certain) {
+            exact_scan_top2(a4, tbase, n_train, lane, d0, d1, j0, j1);
+            result = ((double)__fdiv_rn(d0, d1) < ratio) ? j0 : EACHAM_NONE;
+            if (lane == 0 && fallbacks != nullptr) atomicAdd(fallbacks, 1u);
+        }
+    }
+    if (dbg_idx != nullptr && lane == 0) {
+        dbg_idx[0] = v0 ? (int32_t)j0 : -1; dbg_idx[1] = v1 ? (int32_t)j1 : -1;
+        dbg_dist[0] = d0; dbg_dist[1] = d1;
+    }
+    return result;
 }
 
 // ORB engine: composites carry the exact Hamming distance (an integer) in their high word: ratio test straight from them.
@@ -415,7 +497,8 @@ __global__ void __launch_bounds__(kThreadsTc, 1) tc_match_pairs_kernel(const Pai
         // ===================================== producer =====================================
         if (lane == 0) {
             uint32_t b_it = 0, a_it = 0;
-            for (uint32_t pi = blockIdx.x; pi < p.n_pairs; pi += gridDim.x) {
+            for (uint32_t wk = blockIdx.x; wk < p.n_pairs; wk += gridDim.x) {
+                const uint32_t pi = p.order[wk];
                 const eacham_pair_t pr = p.pairs[pi];
                 const ImageDescTc A = p.images[pr.first], B = p.images[pr.second];
                 if (A.rows == 0 || B.rows == 0) continue;
@@ -445,7 +528,8 @@ __global__ void __launch_bounds__(kThreadsTc, 1) tc_match_pairs_kernel(const Pai
             const uint64_t dbase = tc::make_smem_desc_base(tc::kLBO, tc::kSBO);
             const uint32_t idesc = kOrb ? tc::make_idesc_e4m3_f32(128, 128, true) : tc::make_idesc_bf16_f32(128, 128, true);
             uint32_t b_it = 0, a_it = 0, acc_it = 0;
-            for (uint32_t pi = blockIdx.x; pi < p.n_pairs; pi += gridDim.x) {
+            for (uint32_t wk = blockIdx.x; wk < p.n_pairs; wk += gridDim.x) {
+                const uint32_t pi = p.order[wk];
                 const eacham_pair_t pr = p.pairs[pi];
                 const ImageDescTc A = p.images[pr.first], B = p.images[pr.second];
                 if (A.rows == 0 || B.rows == 0) continue;
@@ -487,7 +571,8 @@ __global__ void __launch_bounds__(kThreadsTc, 1) tc_match_pairs_kernel(const Pai
         uint32_t* m12 = reinterpret_cast<uint32_t*>(my_scratch + (size_t)p.cols_cap * 16);     // [rows_cap]
         uint32_t* m21 = m12 + p.rows_cap;                                                      // [cols_cap]
         uint32_t acc_it = 0;
-        for (uint32_t pi = blockIdx.x; pi < p.n_pairs; pi += gridDim.x) {
+        for (uint32_t wk = blockIdx.x; wk < p.n_pairs; wk += gridDim.x) {
+            const uint32_t pi = p.order[wk];
             const eacham_pair_t pr = p.pairs[pi];
             const ImageDescTc A = p.images[pr.first], B = p.images[pr.second];
             const uint32_t N = A.rows, M = B.rows;
@@ -501,6 +586,7 @@ __global__ void __launch_bounds__(kThreadsTc, 1) tc_match_pairs_kernel(const Pai
             }
             const float* Af = reinterpret_cast<const float*>(p.arena + A.offset);
             const float* Bf = reinterpret_cast<const float*>(p.arena + B.offset);
+            const bool both_exact = A.bf16_exact != 0 && B.bf16_exact != 0;
             const uint32_t na128 = (N + 127) / 128, nbt = (M + 127) / 128;
             for (uint32_t j = et; j < nbt * 128; j += kEpiThreads) { colstate[2 * j] = kEmptyComp; colstate[2 * j + 1] = kEmptyComp; }
             epi_bar();
@@ -594,7 +680,9 @@ __global__ void __launch_bounds__(kThreadsTc, 1) tc_match_pairs_kernel(const Pai
                     const uint32_t lr = e * (kABlockRows / kEpiWarps) + r, row = ab * kABlockRows + lr;
                     if (row < N) {
                         const uint2 cand = S.rowcand[lr];
-                        const uint32_t mm = rerank_ratio(Af + (size_t)row * 128, Bf, cand.x, cand.y, M, p.ratio, lane);
+                        const uint32_t mm = rerank_ratio_checked(Af + (size_t)row * 128, Bf, cand.x, cand.y, M, p.ratio, lane, both_exact, __uint_as_float(B.max_norm_bits),
+                                                                 p.exact_fallbacks, p.dbg_idx12 ? p.dbg_idx12 + 2 * (size_t)row : nullptr,
+                                                                 p.dbg_dist12 ? p.dbg_dist12 + 2 * (size_t)row : nullptr);
                         if (lane == 0) m12[row] = mm;
                     }
                 }
@@ -608,7 +696,9 @@ __global__ void __launch_bounds__(kThreadsTc, 1) tc_match_pairs_kernel(const Pai
             } else {
                 for (uint32_t j = e; j < M; j += kEpiWarps) {
                     const long long k0 = colstate[2 * j], k1 = colstate[2 * j + 1];
-                    const uint32_t mm = rerank_ratio(Bf + (size_t)j * 128, Af, (uint32_t)k0, (uint32_t)k1, N, p.ratio, lane);
+                    const uint32_t mm = rerank_ratio_checked(Bf + (size_t)j * 128, Af, (uint32_t)k0, (uint32_t)k1, N, p.ratio, lane, both_exact, __uint_as_float(A.max_norm_bits),
+                                                             p.exact_fallbacks, p.dbg_idx21 ? p.dbg_idx21 + 2 * (size_t)j : nullptr,
+                                                             p.dbg_dist21 ? p.dbg_dist21 + 2 * (size_t)j : nullptr);
                     if (lane == 0) m21[j] = mm;
                 }
             }

@@ -185,7 +185,7 @@ __global__ void __launch_bounds__(kThreads, 1) orb_tc_match_pairs_kernel(const P
                 uint32_t pi = 0;
                 if (lane == 0) {
                     pi = atomicAdd(p.work_counter, 1u);
-                    if (pi >= p.n_pairs) pi = kNoPair;
+                    pi = pi < p.n_pairs ? p.order[pi] : kNoPair;
                     S.ring[rs] = pi;
                     tc::mbar_arrive(&S.ring_full[rs]);
                 }

@@ -229,7 +229,21 @@ class FeatureMatcherGpu:
         t = L.Timing()
         L.check(self._lib.eacham_gpu_last_timing(self._h, ctypes.byref(t)))
         return dict(upload_ms=t.upload_ms, pairs_h2d_ms=t.pairs_h2d_ms, kernel_ms=t.kernel_ms, d2h_ms=t.d2h_ms,
-                    kernel_launches=int(t.kernel_launches), prep_ms=t.prep_ms)
+                    kernel_launches=int(t.kernel_launches), prep_ms=t.prep_ms, exact_fallbacks=int(t.exact_fallbacks))
+
+    def DebugPairKnn2(self, first: int, second: int):
+        """(idx12[n1,2], dist12[n1,2], idx21[n2,2], dist21[n2,2]): the kNN(k=2) the batched tensor-core SIFT path's ratio test saw
+        for one uploaded pair (see eacham_gpu_debug_pair_knn2)."""
+        k1 = ctypes.c_int(); n1 = ctypes.c_uint32(); k2 = ctypes.c_int(); n2 = ctypes.c_uint32()
+        L.check(self._lib.eacham_gpu_image_info(self._h, first, ctypes.byref(k1), ctypes.byref(n1), None))
+        L.check(self._lib.eacham_gpu_image_info(self._h, second, ctypes.byref(k2), ctypes.byref(n2), None))
+        i12 = np.full((n1.value, 2), -1, np.int32); d12 = np.full((n1.value, 2), np.inf, np.float32)
+        i21 = np.full((n2.value, 2), -1, np.int32); d21 = np.full((n2.value, 2), np.inf, np.float32)
+        opts = self._opts(True)
+        L.check(self._lib.eacham_gpu_debug_pair_knn2(self._h, first, second, ctypes.byref(opts), i12.ctypes.data_as(ctypes.c_void_p),
+                                                     d12.ctypes.data_as(ctypes.c_void_p), i21.ctypes.data_as(ctypes.c_void_p),
+                                                     d21.ctypes.data_as(ctypes.c_void_p)))
+        return i12, d12, i21, d21
 
     def flush_l2(self, nbytes: int = 256 << 20) -> None:
         L.check(self._lib.eacham_gpu_flush_l2(self._h, nbytes))

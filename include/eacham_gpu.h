@@ -115,6 +115,8 @@ typedef struct eacham_gpu_timing {
     float d2h_ms;       /* results + compacted matches D2H                                                    */
     uint32_t kernel_launches; /* kernels launched by the last match_pairs                                     */
     float prep_ms;      /* tensor-core operand copy of the arena (bf16 / one e4m3 per bit), built once after a commit */
+    uint32_t exact_fallbacks; /* F32X128 tensor engine: queries of the last batch re-done by the exact FP32 scan (see below) */
+    uint32_t reserved;
 } eacham_gpu_timing;
 
 EACHAM_API int eacham_gpu_abi_version(void);
@@ -158,6 +160,14 @@ EACHAM_API int eacham_gpu_knn2(eacham_gpu_handle* h, int kind, const void* query
 EACHAM_API int eacham_gpu_match_pairs(eacham_gpu_handle* h, const eacham_pair_t* pairs, size_t n_pairs,
                            const eacham_match_opts* opts, eacham_pair_result_t* res, eacham_match_t* buf,
                            size_t buf_cap, size_t* buf_used);
+
+/* Debug view of the batched tensor-core path for ONE F32X128 pair: the kNN(k=2) its ratio test saw, for the rows of `first`
+ * against `second` (idx12[n1][2], dist12[n1][2]) and the other way round (idx21[n2][2], dist21[n2][2]); -1 / +inf = absent.
+ * dist is the reference's float sqrt(sum (a-b)^2). Where the certainty check (below) sends a query to the exact scan the entries
+ * are the exact matcher's; elsewhere entry 1 is the scorer's second candidate, whose distance can exceed the true second-best
+ * by at most the stated bound -- never enough to change the ratio test's outcome. */
+EACHAM_API int eacham_gpu_debug_pair_knn2(eacham_gpu_handle* h, uint32_t first, uint32_t second, const eacham_match_opts* opts,
+                                          int32_t* idx12, float* dist12, int32_t* idx21, float* dist21);
 
 /* Same computation with inputs AND outputs resident in HBM: enqueue, wait, no D2H of matches.
  * Used by bench.py for the device-resident throughput figure; results stay readable via _fetch. */

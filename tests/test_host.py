@@ -33,7 +33,7 @@ def test_struct_layouts_match_header():
     assert np.dtype(L.MATCH_DTYPE).itemsize == 8
     assert np.dtype(L.PAIR_DTYPE).itemsize == 8
     assert np.dtype(L.RESULT_DTYPE).itemsize == 32
-    assert ctypes.sizeof(L.MatchOpts) == 24 and ctypes.sizeof(L.Config) == 24 and ctypes.sizeof(L.Timing) == 24
+    assert ctypes.sizeof(L.MatchOpts) == 24 and ctypes.sizeof(L.Config) == 24 and ctypes.sizeof(L.Timing) == 32
     assert ctypes.sizeof(L.MultiTiming) == 32
 
 
