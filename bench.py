@@ -426,24 +426,42 @@ def run_single_gpu_workload(env, name, steps, warmup, e2e_steps, cpu_budget_s, o
         rec["engines"] = engines
 
     if with_match_api:
-        # the reference-shaped per-call route: Match(d1, d2), one direction at a time, 4 concurrent callers
-        n_calls = 256 if kind == "orb" else 32
-        m.Match(images[0], images[1])
-        lock_free = [None] * 4
+        # The reference-shaped per-call route driven the way apps/sfm/main.cpp:84-109 drives it: Match(d1, d2)
+        # for every ORDERED pair of a node set, from 4 concurrent callers on one matcher object. The first pass over the set is not
+        # timed (it uploads each image once: the device-side descriptor cache); the timed pass is the steady state of that loop.
+        n_set = min(n_images, 24 if kind == "orb" else 12)
+        calls = [(i, j) for i in range(n_set) for j in range(n_set) if i != j]
 
-        def caller(w):
-            for c in range(w, n_calls, 4):
-                i = c % (n_images - 1)
-                m.Match(images[i], images[i + 1]) if c % 2 == 0 else m.Match(images[i + 1], images[i])
+        # arguments are marshalled once; the timed loop is the C-ABI call itself (ctypes releases the GIL for its duration), which is
+        # what a C++ caller of include/eacham/FeatureMatcherGpu.h sees
+        import ctypes
+        from eacham_b200 import _lib as L
+        from eacham_b200.matcher import _kind_of, _rows_ptr
+        lib = L.load()
+        prepared = []
+        for (i, j) in calls:
+            q, qp, qn, qs = _rows_ptr(images[i]); t, tp, tn, ts = _rows_ptr(images[j])
+            out = np.empty(max(qn, 1), dtype=L.MATCH_DTYPE)
+            prepared.append((_kind_of(q), qp, qn, qs, tp, tn, ts, out, out.ctypes.data_as(ctypes.c_void_p), ctypes.c_size_t()))
 
-        t0 = time.perf_counter()
-        th = [threading.Thread(target=caller, args=(w,)) for w in range(4)]
-        [t.start() for t in th]; [t.join() for t in th]
-        dt = time.perf_counter() - t0
-        rec["match_api"] = {"calls_per_s": n_calls / dt, "pairs_per_s": n_calls / dt / 2, "calls": n_calls, "concurrent_callers": 4,
-                            "note": "eacham_gpu_match: host descriptors in, ratio-filtered map out, per call; the drop-in for "
-                                    "FeatureMatcherFlann::Match with the reference's own loop (main.cpp:98-109 calls it concurrently)"}
-        del lock_free
+        def run_calls(n_threads):
+            def caller(w):
+                for c in range(w, len(prepared), n_threads):
+                    k, qp, qn, qs, tp, tn, ts, out, outp, n = prepared[c]
+                    L.check(lib.eacham_gpu_match(m._h, k, qp, qn, qs, tp, tn, ts, 0.8, outp, out.shape[0], ctypes.byref(n)))
+            t0 = time.perf_counter()
+            th = [threading.Thread(target=caller, args=(w,)) for w in range(n_threads)]
+            [t.start() for t in th]; [t.join() for t in th]
+            return time.perf_counter() - t0
+
+        cold_s = run_calls(4)
+        dt4 = run_calls(4)
+        dt1 = run_calls(1)
+        rec["match_api"] = {"calls_per_s": len(calls) / dt4, "pairs_per_s": len(calls) / dt4 / 2, "calls": len(calls), "concurrent_callers": 4,
+                            "images_in_set": n_set, "one_caller_calls_per_s": len(calls) / dt1, "first_pass_calls_per_s": len(calls) / cold_s,
+                            "note": "eacham_gpu_match: host descriptors in, ratio-filtered map out, per call (one direction); the drop-in for "
+                                    "FeatureMatcherFlann::Match with the reference's own loop over all ordered pairs (main.cpp:84-109). "
+                                    "pairs_per_s = calls / 2. first_pass = the same loop with a cold device cache (each image uploaded once)"}
     m.close()
     return rec
 

@@ -6,6 +6,7 @@
 // pair loop (/root/reference/apps/sfm/main.cpp:84-147). No torch types, no exceptions across the boundary,
 // no CPU fallback.
 #include <algorithm>
+#include <condition_variable>
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
@@ -127,6 +128,26 @@ struct eacham_gpu_handle {
 
     cudaEvent_t ev[8] = {};
     eacham_gpu_timing timing = {};
+
+    // ---- the per-call Match() route on the tensor-core engines (match_single.cuh) ----
+    struct CacheEntry {                       // one image's descriptors, resident on the device across calls
+        const void* host = nullptr; uint32_t rows = 0; size_t stride = 0; int kind = -1; uint64_t hash = 0;
+        DevBuf<uint8_t> raw, tc;
+        int refs = 0; bool ready = false, loading = false; uint64_t tick = 0;
+    };
+    struct CallSlot {                         // what one in-flight Match() call needs privately
+        cudaStream_t stream = nullptr;
+        DevBuf<uint32_t> d_out, d_counter; DevBuf<eacham_pair_t> d_pair;
+        uint32_t* h_out = nullptr; size_t h_out_cap = 0; eacham_pair_t* h_pair = nullptr;
+        bool busy = false;
+    };
+    static constexpr int kCacheEntries = 128, kCallSlots = 8;
+    std::mutex cache_mu;
+    std::condition_variable cache_cv;
+    std::vector<CacheEntry> cache;
+    DevBuf<eacham::tcm::ImageDescTc> d_cache_descs;      // entry i's image record (absolute device addresses)
+    std::vector<CallSlot> slots;
+    uint64_t cache_tick = 0, cache_hits = 0, cache_misses = 0;
 };
 
 namespace {
@@ -249,6 +270,14 @@ void eacham_gpu_destroy(eacham_gpu_handle* h) {
         h->d_counter.release(); h->d_cursor.release(); h->d_q.release(); h->d_t.release(); h->d_partial.release();
         h->d_idx.release(); h->d_dist.release(); h->d_match.release(); h->d_match2.release(); h->d_flush.release();
         if (h->staging) cudaFreeHost(h->staging);
+        for (auto& c : h->cache) { c.raw.release(); c.tc.release(); }
+        h->d_cache_descs.release();
+        for (auto& sl : h->slots) {
+            if (sl.stream) { cudaStreamSynchronize(sl.stream); cudaStreamDestroy(sl.stream); }
+            sl.d_out.release(); sl.d_counter.release(); sl.d_pair.release();
+            if (sl.h_out) cudaFreeHost(sl.h_out);
+            if (sl.h_pair) cudaFreeHost(sl.h_pair);
+        }
         for (auto& e : h->ev) if (e) cudaEventDestroy(e);
         if (h->stream) cudaStreamDestroy(h->stream);
     }
@@ -382,6 +411,10 @@ int eacham_gpu_flush_l2(eacham_gpu_handle* h, size_t bytes) {
 // -------------------------------------------------------------------------------------------------------------
 namespace {
 
+bool match_single_eligible(eacham_gpu_handle* h, int kind, double ratio, size_t q_stride, size_t t_stride);
+int match_single_tc(eacham_gpu_handle* h, int kind, const void* query, uint32_t q_rows, size_t q_stride, const void* train, uint32_t t_rows,
+                    size_t t_stride, double ratio, eacham_match_t* out, size_t cap, size_t* n_out);
+
 // kNN-2 of q (device, nq rows) in t (device, nt rows); outputs on device. Any of idx/dist, match may be null.
 int knn2_device(eacham_gpu_handle* h, int kind, const void* dq, uint32_t nq, const void* dt, uint32_t nt, double ratio,
                 int32_t* d_idx, float* d_dist, uint32_t* d_match, uint32_t* launches) {
@@ -463,6 +496,8 @@ int eacham_gpu_match(eacham_gpu_handle* h, int kind, const void* query, uint32_t
     if (q_rows > 65535u || t_rows > 65535u) return fail(EACHAM_ERR_TOO_LARGE, "at most 65535 descriptors per image");
     *n_out = 0;
     if (q_rows == 0 || t_rows == 0) return EACHAM_OK;
+    if (match_single_eligible(h, kind, ratio, q_stride, t_stride))
+        return match_single_tc(h, kind, query, q_rows, q_stride, train, t_rows, t_stride, ratio, out, cap, n_out);
     std::lock_guard<std::mutex> lk(h->mu);
     DeviceGuard g(h->device);
     int rc;
@@ -626,6 +661,7 @@ int launch_pairs(eacham_gpu_handle* h, const eacham_pair_t* pairs, size_t n_pair
             p.scratch = h->tc_scratch.p;
             p.work_counter = h->d_counter.p; p.order = h->d_order.p; p.exact_fallbacks = h->d_counter.p + 1;
             p.dbg_idx12 = p.dbg_idx21 = nullptr; p.dbg_dist12 = p.dbg_dist21 = nullptr;
+            p.single_dir = 0; p.single_out = nullptr;
             if (h->dbg_on && n_pairs == 1) {
                 p.dbg_idx12 = h->d_dbg_idx.p; p.dbg_dist12 = h->d_dbg_dist.p;
                 p.dbg_idx21 = h->d_dbg_idx.p + 2 * (size_t)max_first; p.dbg_dist21 = h->d_dbg_dist.p + 2 * (size_t)max_first;
@@ -772,4 +808,5 @@ extern "C" int eacham_gpu_debug_pair_knn2(eacham_gpu_handle* h, uint32_t first, 
     return EACHAM_OK;
 }
 
+#include "match_single.cuh"
 #include "multi.cuh"

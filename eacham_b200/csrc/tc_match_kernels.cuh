@@ -120,9 +120,9 @@ __device__ __forceinline__ void orb_tc_prep_row(const uint8_t* __restrict__ src,
 
 // one image at a time (tools / unit tests); grid covers n_blocks * 128 rows, one warp per row
 __global__ void __launch_bounds__(256) sift_prep_kernel(const float* __restrict__ src, uint32_t rows, uint8_t* __restrict__ dst,
-                                                        uint32_t n_blocks) {
+                                                        uint32_t n_blocks, uint32_t* max_norm_bits = nullptr, uint32_t* bf16_exact = nullptr) {
     const uint32_t row = blockIdx.x * 8 + (threadIdx.x >> 5);
-    if (row < n_blocks * tc::kBlockRows) sift_prep_row(src, rows, dst, row, threadIdx.x & 31);
+    if (row < n_blocks * tc::kBlockRows) sift_prep_row(src, rows, dst, row, threadIdx.x & 31, max_norm_bits, bf16_exact);
 }
 __global__ void __launch_bounds__(256) orb_tc_prep_kernel(const uint8_t* __restrict__ src, uint32_t rows, uint8_t* __restrict__ dst,
                                                           uint32_t n_blocks) {
@@ -195,6 +195,11 @@ struct PairParamsTc {
     uint32_t* exact_fallbacks;      // F32X128: number of queries re-done by the exact scan (statistics)
     // debug (single-pair calls, F32X128): the kNN(k=2) the ratio test saw, per row of `first` / of `second`: idx[n][2], dist[n][2]
     int32_t* dbg_idx12; float* dbg_dist12; int32_t* dbg_idx21; float* dbg_dist21;
+    // single-direction mode (the reference-shaped Match(): FeatureMatcherFlann.cpp:14-30). pairs[0] is THE pair; the n_pairs work
+    // items are its 128-row blocks of `first`, one CTA each; only the row direction is evaluated and single_out[row] receives the
+    // ratio-passing train index or EACHAM_NONE. Offsets in the image table are absolute device addresses then (arena = tc_arena = 0).
+    uint32_t single_dir;
+    uint32_t* single_out;
 };
 
 constexpr int kEpiWarps = 16;          // 4 per TMEM lane quadrant, 32 columns of every tile each
@@ -376,7 +381,7 @@ __device__ __forceinline__ int32_t make_key(uint32_t v, uint32_t mask, uint32_t 
     return (int32_t)r;
 }
 
-template <int NH>
+template <int NH, bool kCols>
 __device__ __forceinline__ void epi_tile(uint32_t acc_taddr, int cp, int q, int lane, int32_t (&m0)[2], int32_t (&m1)[2],
                                          uint2* __restrict__ slot_q) {
     const uint32_t ridx0 = q * 32 + lane, ridx1 = 128 + q * 32 + lane;
@@ -394,19 +399,23 @@ __device__ __forceinline__ void epi_tile(uint32_t acc_taddr, int cp, int q, int 
             const int32_t kr0 = make_key(v0[k], mask, idx);
             m1[0] = min(m1[0], max(m0[0], kr0));
             m0[0] = min(m0[0], kr0);
-            int32_t lo = make_key(v0[k], mask, ridx0), hi = kEmptyKeyTc;
+            int32_t lo = kCols ? make_key(v0[k], mask, ridx0) : 0, hi = kEmptyKeyTc;
             if (NH == 2) {
                 const int32_t kr1 = make_key(v1[k], mask, idx);
                 m1[1] = min(m1[1], max(m0[1], kr1));
                 m0[1] = min(m0[1], kr1);
-                const int32_t kc1 = make_key(v1[k], mask, ridx1);
-                hi = max(lo, kc1);
-                lo = min(lo, kc1);
+                if (kCols) {
+                    const int32_t kc1 = make_key(v1[k], mask, ridx1);
+                    hi = max(lo, kc1);
+                    lo = min(lo, kc1);
+                }
             }
-            const int32_t g0 = __reduce_min_sync(0xffffffffu, lo);
-            const int32_t x = (lo == g0) ? hi : lo;
-            const int32_t g1 = __reduce_min_sync(0xffffffffu, x);
-            slot_q[cp * kColsPerWarp + idx] = make_uint2((uint32_t)g0, (uint32_t)g1);   // warp-uniform value: all lanes store the same word
+            if (kCols) {
+                const int32_t g0 = __reduce_min_sync(0xffffffffu, lo);
+                const int32_t x = (lo == g0) ? hi : lo;
+                const int32_t g1 = __reduce_min_sync(0xffffffffu, x);
+                slot_q[cp * kColsPerWarp + idx] = make_uint2((uint32_t)g0, (uint32_t)g1);   // warp-uniform value: all lanes store the same word
+            }
         }
     }
 }
@@ -495,70 +504,83 @@ __global__ void __launch_bounds__(kThreadsTc, 1) tc_match_pairs_kernel(const Pai
 
     if (warp == 0) {
         // ===================================== producer =====================================
-        if (lane == 0) {
+        // the whole warp walks the loop (warp-uniform control flow); one elected lane issues the copies (tc::elect_one)
+        {
             uint32_t b_it = 0, a_it = 0;
             for (uint32_t wk = blockIdx.x; wk < p.n_pairs; wk += gridDim.x) {
-                const uint32_t pi = p.order[wk];
-                const eacham_pair_t pr = p.pairs[pi];
+                const uint32_t pi = p.single_dir ? wk : p.order[wk];
+                const eacham_pair_t pr = p.pairs[p.single_dir ? 0u : pi];
                 const ImageDescTc A = p.images[pr.first], B = p.images[pr.second];
                 if (A.rows == 0 || B.rows == 0) continue;
                 const uint32_t na128 = (A.rows + 127) / 128, nbt = (B.rows + 127) / 128;
                 const uint8_t* Ab = p.tc_arena + A.tc_offset;
                 const uint8_t* Bb = p.tc_arena + B.tc_offset;
-                for (uint32_t ab = 0; ab * 2 < na128; ++ab, ++a_it) {
-                    const uint32_t nh = min(2u, na128 - ab * 2);
+                for (uint32_t ab = p.single_dir ? pi : 0u, ab1 = p.single_dir ? pi + 1 : (na128 + 1) / 2; ab < ab1; ++ab, ++a_it) {
+                    const uint32_t blk0 = p.single_dir ? pi : ab * 2;                     // first 128-row block of this work unit
+                    const uint32_t nh = p.single_dir ? 1u : min(2u, na128 - ab * 2); (void)blk0;
                     tc::mbar_wait(&S.a_empty, (a_it & 1) ^ 1);
-                    tc::mbar_expect_tx(&S.a_full, nh * tc::kAOperandBytes);
-                    for (uint32_t h = 0; h < nh; ++h)
-                        tc::bulk_g2s(S.a[h], Ab + (size_t)(ab * 2 + h) * tc::kBlockBytes, tc::kAOperandBytes, &S.a_full);
+                    if (tc::elect_one()) {
+                        tc::mbar_expect_tx(&S.a_full, nh * tc::kAOperandBytes);
+                        for (uint32_t h = 0; h < nh; ++h)
+                            tc::bulk_g2s(S.a[h], Ab + (size_t)(blk0 + h) * tc::kBlockBytes, tc::kAOperandBytes, &S.a_full);
+                    }
+                    __syncwarp();
                     for (uint32_t bt = 0; bt < nbt; ++bt, ++b_it) {
                         const uint32_t st = b_it % kBStages;
                         tc::mbar_wait(&S.b_empty[st], ((b_it / kBStages) & 1) ^ 1);
-                        tc::mbar_expect_tx(&S.b_full[st], tc::kAOperandBytes);
-                        const uint8_t* src = Bb + (size_t)bt * tc::kBlockBytes;
-                        tc::bulk_g2s(S.b[st], src, tc::kDataBytes, &S.b_full[st]);
-                        tc::bulk_g2s(S.b[st] + tc::kDataBytes, src + tc::kDataBytes + tc::kAugBytes, tc::kAugBytes, &S.b_full[st]);
+                        if (tc::elect_one()) {
+                            tc::mbar_expect_tx(&S.b_full[st], tc::kAOperandBytes);
+                            const uint8_t* src = Bb + (size_t)bt * tc::kBlockBytes;
+                            tc::bulk_g2s(S.b[st], src, tc::kDataBytes, &S.b_full[st]);
+                            tc::bulk_g2s(S.b[st] + tc::kDataBytes, src + tc::kDataBytes + tc::kAugBytes, tc::kAugBytes, &S.b_full[st]);
+                        }
+                        __syncwarp();
                     }
                 }
             }
         }
     } else if (warp == 1) {
         // ===================================== MMA issuer =====================================
-        if (lane == 0) {
+        // whole warp in the loop, one elected lane issues: no ELECT / BRA.U.ANY waterfall around every tcgen05.mma
+        {
             const uint64_t dbase = tc::make_smem_desc_base(tc::kLBO, tc::kSBO);
             const uint32_t idesc = kOrb ? tc::make_idesc_e4m3_f32(128, 128, true) : tc::make_idesc_bf16_f32(128, 128, true);
             uint32_t b_it = 0, a_it = 0, acc_it = 0;
             for (uint32_t wk = blockIdx.x; wk < p.n_pairs; wk += gridDim.x) {
-                const uint32_t pi = p.order[wk];
-                const eacham_pair_t pr = p.pairs[pi];
+                const uint32_t pi = p.single_dir ? wk : p.order[wk];
+                const eacham_pair_t pr = p.pairs[p.single_dir ? 0u : pi];
                 const ImageDescTc A = p.images[pr.first], B = p.images[pr.second];
                 if (A.rows == 0 || B.rows == 0) continue;
                 const uint32_t na128 = (A.rows + 127) / 128, nbt = (B.rows + 127) / 128;
-                for (uint32_t ab = 0; ab * 2 < na128; ++ab, ++a_it) {
-                    const uint32_t nh = min(2u, na128 - ab * 2);
+                for (uint32_t ab = p.single_dir ? pi : 0u, ab1 = p.single_dir ? pi + 1 : (na128 + 1) / 2; ab < ab1; ++ab, ++a_it) {
+                    const uint32_t blk0 = p.single_dir ? pi : ab * 2;                     // first 128-row block of this work unit
+                    const uint32_t nh = p.single_dir ? 1u : min(2u, na128 - ab * 2); (void)blk0;
                     tc::mbar_wait(&S.a_full, a_it & 1);
                     for (uint32_t bt = 0; bt < nbt; ++bt, ++b_it, ++acc_it) {
                         const uint32_t st = b_it % kBStages, as = acc_it % kAccStages;
                         tc::mbar_wait(&S.b_full[st], (b_it / kBStages) & 1);
                         tc::mbar_wait(&S.acc_empty[as], ((acc_it / kAccStages) & 1) ^ 1);
                         tc::tc_fence_after();
-                        const uint32_t b_addr = tc::smem_u32(S.b[st]);
-                        for (uint32_t h = 0; h < nh; ++h) {
-                            const uint32_t a_addr = tc::smem_u32(S.a[h]);
-                            const uint32_t d = tmem + as * 256 + h * 128;
+                        if (tc::elect_one()) {
+                            const uint32_t b_addr = tc::smem_u32(S.b[st]);
+                            for (uint32_t h = 0; h < nh; ++h) {
+                                const uint32_t a_addr = tc::smem_u32(S.a[h]);
+                                const uint32_t d = tmem + as * 256 + h * 128;
 #pragma unroll
-                            for (int ks = 0; ks < tc::kKSteps; ++ks)
-                            {
-                                const uint64_t da = tc::smem_desc(dbase, a_addr + ks * 2 * tc::kChunkStride);
-                                const uint64_t db = tc::smem_desc(dbase, b_addr + ks * 2 * tc::kChunkStride);
-                                if (kOrb) tc::mma_f8(d, da, db, idesc, ks > 0);
-                                else tc::mma_bf16(d, da, db, idesc, ks > 0);
+                                for (int ks = 0; ks < tc::kKSteps; ++ks) {
+                                    const uint64_t da = tc::smem_desc(dbase, a_addr + ks * 2 * tc::kChunkStride);
+                                    const uint64_t db = tc::smem_desc(dbase, b_addr + ks * 2 * tc::kChunkStride);
+                                    if (kOrb) tc::mma_f8(d, da, db, idesc, ks > 0);
+                                    else tc::mma_bf16(d, da, db, idesc, ks > 0);
+                                }
                             }
+                            tc::mma_commit(&S.b_empty[st]);      // B stage reusable once these MMAs have read it
+                            tc::mma_commit(&S.acc_full[as]);     // accumulators ready for the epilogue
                         }
-                        tc::mma_commit(&S.b_empty[st]);      // B stage reusable once these MMAs have read it
-                        tc::mma_commit(&S.acc_full[as]);     // accumulators ready for the epilogue
+                        __syncwarp();
                     }
-                    tc::mma_commit(&S.a_empty);              // A block reusable
+                    if (tc::elect_one()) tc::mma_commit(&S.a_empty);              // A block reusable
+                    __syncwarp();
                 }
             }
         }
@@ -572,8 +594,8 @@ __global__ void __launch_bounds__(kThreadsTc, 1) tc_match_pairs_kernel(const Pai
         uint32_t* m21 = m12 + p.rows_cap;                                                      // [cols_cap]
         uint32_t acc_it = 0;
         for (uint32_t wk = blockIdx.x; wk < p.n_pairs; wk += gridDim.x) {
-            const uint32_t pi = p.order[wk];
-            const eacham_pair_t pr = p.pairs[pi];
+            const uint32_t pi = p.single_dir ? wk : p.order[wk];
+            const eacham_pair_t pr = p.pairs[p.single_dir ? 0u : pi];
             const ImageDescTc A = p.images[pr.first], B = p.images[pr.second];
             const uint32_t N = A.rows, M = B.rows;
             if (N == 0 || M == 0) {
@@ -588,11 +610,14 @@ __global__ void __launch_bounds__(kThreadsTc, 1) tc_match_pairs_kernel(const Pai
             const float* Bf = reinterpret_cast<const float*>(p.arena + B.offset);
             const bool both_exact = A.bf16_exact != 0 && B.bf16_exact != 0;
             const uint32_t na128 = (N + 127) / 128, nbt = (M + 127) / 128;
+            const bool cols = !p.single_dir;
+            if (cols)
             for (uint32_t j = et; j < nbt * 128; j += kEpiThreads) { colstate[2 * j] = kEmptyComp; colstate[2 * j + 1] = kEmptyComp; }
             epi_bar();
 
-            for (uint32_t ab = 0; ab * 2 < na128; ++ab) {
-                const uint32_t nh = min(2u, na128 - ab * 2);
+            for (uint32_t ab = p.single_dir ? pi : 0u, ab1 = p.single_dir ? pi + 1 : (na128 + 1) / 2; ab < ab1; ++ab) {
+                const uint32_t blk0 = p.single_dir ? pi : ab * 2;                     // first 128-row block of this work unit
+                    const uint32_t nh = p.single_dir ? 1u : min(2u, na128 - ab * 2); (void)blk0;
                 int32_t m0[2] = {kEmptyKeyTc, kEmptyKeyTc}, m1[2] = {kEmptyKeyTc, kEmptyKeyTc};
                 uint32_t m0x2 = 0xFFFFFFFFu, m1x2 = 0xFFFFFFFFu;           // ORB: packed 16-bit row keys of both rows
                 uint32_t t0[2] = {0xFFFFu, 0xFFFFu}, t1[2] = {0xFFFFu, 0xFFFFu};
@@ -600,7 +625,7 @@ __global__ void __launch_bounds__(kThreadsTc, 1) tc_match_pairs_kernel(const Pai
                     const uint32_t as = acc_it % kAccStages;
                     // column state of this tile: issue the (L2) load early, consumed after the barrier
                     long long c0 = 0, c1 = 0;
-                    if (et < 128) { c0 = colstate[2 * (bt * 128 + et)]; c1 = colstate[2 * (bt * 128 + et) + 1]; }
+                    if (cols && et < 128) { c0 = colstate[2 * (bt * 128 + et)]; c1 = colstate[2 * (bt * 128 + et) + 1]; }
                     if (kOrb) { m0[0] = (int32_t)(m0x2 & 0xFFFFu); m0[1] = (int32_t)(m0x2 >> 16); m1[0] = (int32_t)(m1x2 & 0xFFFFu); m1[1] = (int32_t)(m1x2 >> 16); }
                     const int32_t o00 = m0[0], o10 = m1[0], o01 = m0[1], o11 = m1[1];
                     tc::mbar_wait(&S.acc_full[as], (acc_it / kAccStages) & 1);
@@ -613,8 +638,11 @@ __global__ void __launch_bounds__(kThreadsTc, 1) tc_match_pairs_kernel(const Pai
                         m0[0] = (int32_t)(m0x2 & 0xFFFFu); m0[1] = (int32_t)(m0x2 >> 16);
                         m1[0] = (int32_t)(m1x2 & 0xFFFFu); m1[1] = (int32_t)(m1x2 >> 16);
                     } else {
-                        if (nh == 2) epi_tile<2>(taddr, cp, q, lane, m0, m1, slot_q);
-                        else epi_tile<1>(taddr, cp, q, lane, m0, m1, slot_q);
+                        if (!cols) {               // single-direction mode: rows only
+                            if (nh == 2) epi_tile<2, false>(taddr, cp, q, lane, m0, m1, slot_q);
+                            else epi_tile<1, false>(taddr, cp, q, lane, m0, m1, slot_q);
+                        } else if (nh == 2) epi_tile<2, true>(taddr, cp, q, lane, m0, m1, slot_q);
+                        else epi_tile<1, true>(taddr, cp, q, lane, m0, m1, slot_q);
                     }
                     tc::tc_fence_before();
                     __syncwarp();
@@ -626,8 +654,8 @@ __global__ void __launch_bounds__(kThreadsTc, 1) tc_match_pairs_kernel(const Pai
                         if (m0[h] != om0) { t1[h] = (m1[h] == om0) ? t0[h] : bt; t0[h] = bt; }
                         else if (m1[h] != om1) t1[h] = bt;
                     }
-                    epi_bar();                                              // all 8 warps' slots of this tile are written
-                    if (et < 128) {
+                    if (cols) epi_bar();                                    // all 16 warps' slots of this tile are written
+                    if (cols && et < 128) {
                         long long g0 = kEmptyComp, g1 = kEmptyComp;
 #pragma unroll
                         for (int qq = 0; qq < 4; ++qq) {
@@ -667,8 +695,8 @@ __global__ void __launch_bounds__(kThreadsTc, 1) tc_match_pairs_kernel(const Pai
                             comp_merge(b0, b1, a0, a1);
                         }
                         if (kOrb) {                                   // exact distances are in the keys: no re-rank
-                            const uint32_t row = ab * kABlockRows + h * 128 + q * 32 + lane;
-                            if (row < N) m12[row] = comp_ratio(a0, a1, M, p.ratio);
+                            const uint32_t row = blk0 * 128 + h * 128 + q * 32 + lane;
+                            if (row < N && h < (int)nh) (p.single_dir ? p.single_out : m12)[row] = comp_ratio(a0, a1, M, p.ratio);
                         } else {
                             S.rowcand[h * 128 + q * 32 + lane] = make_uint2((uint32_t)a0, (uint32_t)a1);
                         }
@@ -677,18 +705,19 @@ __global__ void __launch_bounds__(kThreadsTc, 1) tc_match_pairs_kernel(const Pai
                 epi_bar();
                 if (!kOrb)
                 for (int r = 0; r < kABlockRows / kEpiWarps; ++r) {
-                    const uint32_t lr = e * (kABlockRows / kEpiWarps) + r, row = ab * kABlockRows + lr;
-                    if (row < N) {
+                    const uint32_t lr = e * (kABlockRows / kEpiWarps) + r, row = blk0 * 128 + lr;
+                    if (row < N && lr < nh * 128) {
                         const uint2 cand = S.rowcand[lr];
                         const uint32_t mm = rerank_ratio_checked(Af + (size_t)row * 128, Bf, cand.x, cand.y, M, p.ratio, lane, both_exact, __uint_as_float(B.max_norm_bits),
                                                                  p.exact_fallbacks, p.dbg_idx12 ? p.dbg_idx12 + 2 * (size_t)row : nullptr,
                                                                  p.dbg_dist12 ? p.dbg_dist12 + 2 * (size_t)row : nullptr);
-                        if (lane == 0) m12[row] = mm;
+                        if (lane == 0) (p.single_dir ? p.single_out : m12)[row] = mm;
                     }
                 }
                 epi_bar();                                                  // rowkeys / rowcand reusable
             }
 
+            if (p.single_dir) continue;                       // one direction only
             // ---- columns: re-rank, ratio -> m21 ----
             __threadfence_block();
             if (kOrb) {

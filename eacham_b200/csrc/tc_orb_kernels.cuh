@@ -185,25 +185,26 @@ __global__ void __launch_bounds__(kThreads, 1) orb_tc_match_pairs_kernel(const P
                 uint32_t pi = 0;
                 if (lane == 0) {
                     pi = atomicAdd(p.work_counter, 1u);
-                    pi = pi < p.n_pairs ? p.order[pi] : kNoPair;
+                    pi = pi < p.n_pairs ? (p.single_dir ? pi : p.order[pi]) : kNoPair;
                     S.ring[rs] = pi;
                     tc::mbar_arrive(&S.ring_full[rs]);
                 }
                 pi = __shfl_sync(0xffffffffu, pi, 0);
                 if (pi == kNoPair) break;
-                const eacham_pair_t pr = p.pairs[pi];
+                const eacham_pair_t pr = p.pairs[p.single_dir ? 0u : pi];
                 const ImageDescTc A = p.images[pr.first], B = p.images[pr.second];
                 if (A.rows == 0 || B.rows == 0) continue;
                 const uint32_t na128 = (A.rows + 127) / 128, nbt = (B.rows + 127) / 128;
                 const uint8_t* Ab = p.tc_arena + A.tc_offset;
                 const uint8_t* Bb = p.tc_arena + B.tc_offset;
-                for (uint32_t ab = 0; ab * 2 < na128; ++ab, ++a_it) {
-                    const uint32_t nh = min(2u, na128 - ab * 2);
+                for (uint32_t ab = p.single_dir ? pi : 0u, ab1 = p.single_dir ? pi + 1 : (na128 + 1) / 2; ab < ab1; ++ab, ++a_it) {
+                    const uint32_t blk0 = p.single_dir ? pi : ab * 2;                     // first 128-row block of this work unit
+                    const uint32_t nh = p.single_dir ? 1u : min(2u, na128 - ab * 2); (void)blk0;
                     tc::mbar_wait(&S.a_empty, (a_it & 1) ^ 1);
                     if (tc::elect_one()) {
                         tc::mbar_expect_tx(&S.a_full, nh * tc::kAOperandBytes);
                         for (uint32_t h = 0; h < nh; ++h)
-                            tc::bulk_g2s(S.a[h], Ab + (size_t)(ab * 2 + h) * tc::kBlockBytes, tc::kAOperandBytes, &S.a_full);
+                            tc::bulk_g2s(S.a[h], Ab + (size_t)(blk0 + h) * tc::kBlockBytes, tc::kAOperandBytes, &S.a_full);
                     }
                     __syncwarp();
                     for (uint32_t bt = 0; bt < nbt; ++bt, ++b_it) {
@@ -234,12 +235,13 @@ __global__ void __launch_bounds__(kThreads, 1) orb_tc_match_pairs_kernel(const P
                 __syncwarp();
                 if (lane == 0) tc::mbar_arrive(&S.ring_empty[rs]);
                 if (pi == kNoPair) break;
-                const eacham_pair_t pr = p.pairs[pi];
+                const eacham_pair_t pr = p.pairs[p.single_dir ? 0u : pi];
                 const ImageDescTc A = p.images[pr.first], B = p.images[pr.second];
                 if (A.rows == 0 || B.rows == 0) continue;
                 const uint32_t na128 = (A.rows + 127) / 128, nbt = (B.rows + 127) / 128;
-                for (uint32_t ab = 0; ab * 2 < na128; ++ab, ++a_it) {
-                    const uint32_t nh = min(2u, na128 - ab * 2);
+                for (uint32_t ab = p.single_dir ? pi : 0u, ab1 = p.single_dir ? pi + 1 : (na128 + 1) / 2; ab < ab1; ++ab, ++a_it) {
+                    const uint32_t blk0 = p.single_dir ? pi : ab * 2;                     // first 128-row block of this work unit
+                    const uint32_t nh = p.single_dir ? 1u : min(2u, na128 - ab * 2); (void)blk0;
                     tc::mbar_wait(&S.a_full, a_it & 1);
                     for (uint32_t bt = 0; bt < nbt; ++bt, ++b_it, ++acc_it) {
                         const uint32_t st = b_it % kBStages, as = acc_it % kAccStages;
@@ -290,10 +292,11 @@ __global__ void __launch_bounds__(kThreads, 1) orb_tc_match_pairs_kernel(const P
             tc::mbar_wait(&S.ring_full[rs], (k / kRing) & 1);
             const uint32_t pi = S.ring[rs];
             if (pi == kNoPair) break;
-            const eacham_pair_t pr = p.pairs[pi];
+            const eacham_pair_t pr = p.pairs[p.single_dir ? 0u : pi];
             const ImageDescTc A = p.images[pr.first], B = p.images[pr.second];
             const uint32_t N = A.rows, M = B.rows;
             const uint32_t na128 = (N + 127) / 128, nbt = (M + 127) / 128;
+            if (!p.single_dir)
             for (uint32_t j = et; j < nbt * 64 * 4; j += kEpiThreads) colq[(j / (nbt * 64)) * colq_stride + j % (nbt * 64)] = make_uint4(kSentX2, kSentX2, 0u, 0u);
             epi_bar();                                        // every epilogue thread has read the ring slot
             if (et == 0) tc::mbar_arrive(&S.ring_empty[rs]);
@@ -308,8 +311,9 @@ __global__ void __launch_bounds__(kThreads, 1) orb_tc_match_pairs_kernel(const P
             const uint4* Aq = reinterpret_cast<const uint4*>(p.arena + A.offset);
             const uint4* Bq = reinterpret_cast<const uint4*>(p.arena + B.offset);
 
-            for (uint32_t ab = 0; ab * 2 < na128; ++ab) {
-                const uint32_t nh = min(2u, na128 - ab * 2);
+            for (uint32_t ab = p.single_dir ? pi : 0u, ab1 = p.single_dir ? pi + 1 : (na128 + 1) / 2; ab < ab1; ++ab) {
+                const uint32_t blk0 = p.single_dir ? pi : ab * 2;                     // first 128-row block of this work unit
+                    const uint32_t nh = p.single_dir ? 1u : min(2u, na128 - ab * 2); (void)blk0;
                 uint32_t m0[2] = {kSentX2, kSentX2}, m1[2] = {kSentX2, kSentX2};       // packed (even | odd columns) top-2 per row half
                 uint32_t t0[2] = {0u, 0u};                                             // packed f16: tile where m0 last decreased
                 uint32_t btx2 = 0u;                                                    // packed f16 (bt | bt)
@@ -319,7 +323,8 @@ __global__ void __launch_bounds__(kThreads, 1) orb_tc_match_pairs_kernel(const P
                     // this warp's column state of the tile (lane c < 16: column pair c of the part): issue the (L2) load early
                     uint4 cst = make_uint4(kSentX2, kSentX2, 0u, 0u);
                     uint4* cptr = colq + (size_t)q * colq_stride + bt * 64 + cp * (kColsPerWarp / 2) + (lane & 15);
-                    if (lane < 16 && !(EACHAM_EXP & 4)) cst = *cptr;
+                    const bool cols = !p.single_dir;
+                    if (lane < 16 && cols && !(EACHAM_EXP & 4)) cst = *cptr;
                     if (tid == 0) EACHAM_TRACE(0, acc_it, 0);
                     tc::mbar_wait(&S.acc_full[as], (acc_it / kAccStages) & 1);
                     if (tid == 0) EACHAM_TRACE(0, acc_it, 1);
@@ -338,7 +343,7 @@ __global__ void __launch_bounds__(kThreads, 1) orb_tc_match_pairs_kernel(const P
                         for (int i = 0; i < 16; ++i) v1[i] = kSentX2;
                     }
                     // ---- columns: sort-2 across the row halves, transpose, merge over lanes ----
-                    if (!(EACHAM_EXP & 2))
+                    if (cols && !(EACHAM_EXP & 2))
 #pragma unroll
                     for (int i = 0; i < 16; i += 2) {
                         uint32_t l0, h0, l1, h1;
@@ -372,7 +377,7 @@ __global__ void __launch_bounds__(kThreads, 1) orb_tc_match_pairs_kernel(const P
                     }
                     // ---- columns, continued: lane (c, H) merges rows H*16 .. H*16+15 of column pair c ----
                     uint32_t g0 = v0[0], g1 = v1[0];
-                    if (!(EACHAM_EXP & 2)) {
+                    if (cols && !(EACHAM_EXP & 2)) {
                         const int c = lane & 15, H = lane >> 4;
                         const uint2* src = xp + (H * 16) * kXposeStride + c;
                         uint32_t l[8], h[8];
@@ -414,7 +419,7 @@ __global__ void __launch_bounds__(kThreads, 1) orb_tc_match_pairs_kernel(const P
                 {
                     // two threads per row: both merge the parts, each checks 8 of the 16 candidate columns
                     const int qt = cp * 32 + lane, rr = qt >> 1, half = qt & 1, h = rr >> 5, l = rr & 31;
-                    const uint32_t row = ab * kABlockRows + h * 128 + q * 32 + l;
+                    const uint32_t row = blk0 * 128 + h * 128 + q * 32 + l;
                     uint32_t best = 0xFFFFu, second = 0xFFFFu, wt = 0, wid = 0;
 #pragma unroll
                     for (int c = 0; c < kColParts; ++c) {
@@ -428,7 +433,7 @@ __global__ void __launch_bounds__(kThreads, 1) orb_tc_match_pairs_kernel(const P
                         }
                     }
                     uint32_t found = EACHAM_NONE, ham0 = 0;
-                    if (row < N && ratio_pass_f16(best, second, p.ratio, ham0)) {
+                    if (row < N && h < (int)nh && ratio_pass_f16(best, second, p.ratio, ham0)) {
                         // the unique best lives in tile wt, column part wid / 2, column parity wid & 1: 16 candidates
                         const uint32_t tile = (uint32_t)__half2int_rn(__ushort_as_half((unsigned short)wt));
                         const uint32_t base = tile * 128 + (wid >> 1) * kColsPerWarp + (wid & 1) + half * 16;
@@ -440,11 +445,12 @@ __global__ void __launch_bounds__(kThreads, 1) orb_tc_match_pairs_kernel(const P
                         }
                     }
                     found = min(found, __shfl_xor_sync(0xffffffffu, found, 1));
-                    if (half == 0 && row < N) m12[row] = found;
+                    if (half == 0 && row < N && h < (int)nh) (p.single_dir ? p.single_out : m12)[row] = found;
                 }
                 quad_bar(q);                                                // exchange area read: the transpose buffer is free again
             }
 
+            if (p.single_dir) continue;                       // one direction only: the rows of this block are the whole work item
             // ---- columns: merge the four quadrant states, ratio test, recover the row index among the 64 rows of (row block, quadrant) ----
             epi_bar();
             __threadfence_block();

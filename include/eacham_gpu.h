@@ -65,6 +65,8 @@ typedef struct eacham_gpu_handle eacham_gpu_handle;
 #define EACHAM_CFG_ORB_POPC 2u         /* ORB pairs on the XOR+POPC kernel instead of the default tensor-core engine (bits as FP8 0/1, exact) */
 #define EACHAM_CFG_ORB_TC_V1 4u        /* ORB pairs on the round-1 tensor-core kernel (F32 accumulators, 32-bit keys); for A/B measurements   */
 #define EACHAM_CFG_ORB_TC_ALU_SORT 8u  /* default ORB engine with its sort-2 steps on the ALU pipe instead of the FMA pipe; for A/B measurements */
+#define EACHAM_CFG_MATCH_NO_CACHE 32u  /* eacham_gpu_match: do not keep descriptors on the device between calls (see eacham_gpu_match) */
+#define EACHAM_CFG_MATCH_LEGACY 64u    /* eacham_gpu_match on the round-1 CUDA-core kernels (upload both images per call, one call at a time) */
 #define EACHAM_CFG_MULTI_PARALLEL_H2D 16u /* eacham_gpu_create_multi: one H2D copy per device instead of H2D + NCCL broadcast (no NCCL needed) */
 
 typedef struct eacham_gpu_config {
@@ -143,7 +145,13 @@ EACHAM_API int eacham_gpu_arena(eacham_gpu_handle* h, void** device_ptr, size_t*
 EACHAM_API int eacham_gpu_image_info(eacham_gpu_handle* h, uint32_t image_id, int* kind, uint32_t* rows, size_t* arena_offset);
 
 /* One direction, one pair: the reference's Match(). Synchronous, thread-safe. out gets <= cap entries, *n_out the
- * number of ratio-passing matches (sorted by query index); EACHAM_ERR_BUFFER_TOO_SMALL if *n_out > cap. */
+ * number of ratio-passing matches (sorted by query index); EACHAM_ERR_BUFFER_TOO_SMALL if *n_out > cap.
+ * Runs on the tensor-core engines, one CTA per 128 query rows, and up to 8 calls proceed concurrently on their own streams (the
+ * reference calls Match from TBB workers, apps/sfm/main.cpp:98-109). Descriptor matrices stay resident on the device between
+ * calls: the reference passes the same Node-owned cv::Mat for an image in every pair it takes part in (main.cpp:107-108), so an
+ * image is uploaded and converted once, not once per pair. A cached copy is recognised by (pointer, rows, stride, kind) AND a hash
+ * of 16 sampled rows; a caller that rewrites a descriptor matrix in place between calls without touching any sampled row must
+ * create the handle with EACHAM_CFG_MATCH_NO_CACHE. */
 EACHAM_API int eacham_gpu_match(eacham_gpu_handle* h, int kind, const void* query, uint32_t q_rows, size_t q_stride_bytes,
                      const void* train, uint32_t t_rows, size_t t_stride_bytes, double ratio, eacham_match_t* out,
                      size_t cap, size_t* n_out);

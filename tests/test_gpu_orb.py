@@ -255,3 +255,40 @@ def test_match_graph_dump_roundtrip_from_gpu(matcher, tmp_path):
     for (i, j), b12 in edges.items():
         assert b12 == {int(a): int(b) for a, b in O.c_match_pair(imgs[i], imgs[j])["matches"]}
     assert len(edges) > 0
+
+
+@pytest.mark.parametrize("kind", ["orb", "sift"])
+def test_match_route_cache_and_concurrency(kind):
+    """eacham_gpu_match on the tensor-core engines: descriptors cached on the device across calls (keyed by pointer + sampled-row
+    hash), calls from several threads in flight at once. Same answers as the exact CPU matcher, also after a matrix is rewritten in
+    place (a sampled row changes -> re-upload), with the cache switched off, and on the legacy kernels."""
+    import eacham_b200
+    from eacham_b200 import synth
+    if kind == "orb":
+        imgs = synth.orb_image_set(6, 1300, seed=41, pool=3000)
+        imgs[2] = np.ascontiguousarray(imgs[2][:700])
+    else:
+        imgs = synth.sift_image_set(5, 700, seed=42, pool=900)
+        imgs[1] = np.ascontiguousarray(imgs[1][:333])
+    n = len(imgs)
+    want = {(i, j): O.c_match(imgs[i], imgs[j]) for i in range(n) for j in range(n) if i != j}
+    for kw in ({}, {"match_cache": False}, {"match_legacy": True}):
+        with eacham_b200.FeatureMatcherGpu(0.8, **kw) as m:
+            got = {}
+
+            def work(w):
+                for k, (i, j) in enumerate(sorted(want)):
+                    if k % 4 == w:
+                        got[(i, j)] = m.Match(imgs[i], imgs[j])
+
+            th = [threading.Thread(target=work, args=(w,)) for w in range(4)]
+            [t.start() for t in th]; [t.join() for t in th]
+            assert got == want, kw
+            if not kw:
+                # rewrite image 0 in place: its first row is one of the sampled rows, so the cached copy must not be reused
+                old = imgs[0].copy()
+                imgs[0][:] = imgs[3][: imgs[0].shape[0]] if imgs[3].shape[0] >= imgs[0].shape[0] else np.roll(imgs[0], 7, axis=0)
+                assert m.Match(imgs[0], imgs[1]) == O.c_match(imgs[0], imgs[1])
+                assert m.Match(imgs[1], imgs[0]) == O.c_match(imgs[1], imgs[0])
+                imgs[0][:] = old
+                assert m.Match(imgs[0], imgs[1]) == want[(0, 1)]
