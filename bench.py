@@ -345,8 +345,57 @@ def device_timed(env, m, my_pairs, steps, warmup, sample_clocks=False):
     return total_ms, launches, wall_s, clocks
 
 
+def verify_record(m, images, pairs, res, buf, n_hyp=32, cpu_budget_s=6.0):
+    """SURVEY.md 8(f) N1 on the batch that is still resident in HBM: every pair's matches scored under n_hyp essential-matrix and n_hyp
+    homography hypotheses (LMedS median, sigma, inlier count), eacham_gpu_verify_pairs; CPU = the NumPy restatement of OpenCV's scoring."""
+    from eacham_b200 import _lib as L
+    from oracle import verify_oracle as V
+    rng = np.random.default_rng(99)
+    kps = [np.stack([rng.uniform(0, 800, d.shape[0]), rng.uniform(0, 800, d.shape[0])], 1).astype(np.float32) for d in images]
+    for i, k in enumerate(kps):
+        m.SetKeypoints(i, k)
+    f, cx, cy = 700.0, 400.0, 400.0
+    hyp_e = rng.normal(0, 1, (n_hyp, 3, 3))
+    hyp_h = np.eye(3)[None] + rng.normal(0, 0.01, (n_hyp, 3, 3)); hyp_h[:, 2, 2] = 1.0
+    out = {}
+    n_pairs = len(pairs)
+    for model, code, hyps in (("essential", L.MODEL_ESSENTIAL, hyp_e), ("homography", L.MODEL_HOMOGRAPHY, hyp_h)):
+        m.VerifyPairs(code, hyps, f, cx, cy)                                  # warm-up
+        ms, wall = [], []
+        for _ in range(3):
+            t0 = time.perf_counter()
+            vres, _, _ = m.VerifyPairs(code, hyps, f, cx, cy)
+            wall.append(time.perf_counter() - t0)
+            ms.append(m.timing()["verify_ms"])
+        order = np.random.default_rng(5).permutation(n_pairs)[:4096]
+        t0 = time.perf_counter()
+        done = mism = 0
+        for k in order:
+            r = res[k]
+            mm = buf[int(r["offset"]): int(r["offset"] + r["count"])]
+            i, j = int(pairs[k][0]), int(pairs[k][1])
+            want = V.verify_pair(model, hyps, kps[i][mm["query"]], kps[j][mm["train"]], f, cx, cy)
+            mism += (int(vres[k]["best"]), int(vres[k]["n_inliers"]), float(vres[k]["median"])) != (want["best"], want["n_inliers"], float(want["median"]))
+            done += 1
+            if time.perf_counter() - t0 > cpu_budget_s / 2 and done >= 16:
+                break
+        cpu_s = time.perf_counter() - t0
+        matches = int(res["count"].sum())
+        out[model] = {"value": n_pairs / (min(ms) * 1e-3), "unit": "pairs/s", "hypotheses_per_pair": n_hyp, "kernel_ms": min(ms),
+                      "e2e": {"value": n_pairs / min(wall), "unit": "pairs/s", "includes": "hypotheses H2D + kernel + per-pair results D2H (match lists and keypoints already resident)"},
+                      "residuals_per_s": matches * n_hyp / (min(ms) * 1e-3),
+                      "roofline": {"bound": "hbm", "achieved": (matches * 24 + n_pairs * 56) / (min(ms) * 1e-3) / 1e9, "peak": peaks()["hbm_gbs"], "unit": "GB/s",
+                                   "frac": (matches * 24 + n_pairs * 56) / (min(ms) * 1e-3) / 1e9 / peaks()["hbm_gbs"], "traffic": None,
+                                   "note": "algorithmic bytes = match entry (8 B) + two gathered keypoints (16 B) per match + per-pair records; the kernel is bound by "
+                                           "its shared-memory bitonic sorts (one per hypothesis), not by HBM -- see DESIGN.md"},
+                      "cpu_baseline": {"value": done / cpu_s, "unit": "pairs/s", "cores": 1, "kind": "port",
+                                       "sample": f"{done} random pairs of the batch, NumPy restatement of OpenCV's computeError + LMedS (oracle/verify_oracle.py), 1 thread",
+                                       "parity_checked_pairs": done, "parity_mismatches": int(mism)}}
+    return out
+
+
 def run_single_gpu_workload(env, name, steps, warmup, e2e_steps, cpu_budget_s, orb_engine="tensor", sample_clocks=False, images_override=0,
-                            with_engines=False, with_match_api=False):
+                            with_engines=False, with_match_api=False, with_verify=False):
     """One workload on one GPU: value, e2e, roofline, cpu_baseline with in-run parity. Returns the record (and keeps nothing)."""
     import eacham_b200
     kind, n_desc, n_images, _ = WORKLOADS[name]
@@ -404,6 +453,9 @@ def run_single_gpu_workload(env, name, steps, warmup, e2e_steps, cpu_budget_s, o
            "matches_per_step": int(res["count"].sum()), "wall_s_timed_region": wall_s}
     if clocks is not None:
         rec["clocks"] = clocks
+
+    if with_verify:
+        rec["verify"] = verify_record(m, images, pairs, res, buf)
 
     if with_engines and kind == "orb":
         engines = {orb_engine: {"value": value, "unit": "pairs/s", "steps": steps, "default": True}}
@@ -564,7 +616,7 @@ def main():
     kind = WORKLOADS[name][0]
     e2e_steps = max(1, min(args.e2e_steps or args.steps, args.steps))
     main_rec = run_single_gpu_workload(env, name, args.steps, args.warmup, e2e_steps, args.cpu_budget_s, orb_engine=args.orb_engine,
-                                       sample_clocks=True, images_override=args.images, with_engines=True, with_match_api=True)
+                                       sample_clocks=True, images_override=args.images, with_engines=True, with_match_api=True, with_verify=True)
     line = {
         "metric": METRIC if name in ("orb4k", "orb4k5") else f"image pairs matched/sec ({name})",
         "value": main_rec.pop("value"), "unit": "pairs/s", "n_gpus": 1, "steps": args.steps, "warmup": main_rec.pop("warmup"),

@@ -31,7 +31,15 @@ class MatchOpts(ctypes.Structure):
 class Timing(ctypes.Structure):
     _fields_ = [("upload_ms", ctypes.c_float), ("pairs_h2d_ms", ctypes.c_float), ("kernel_ms", ctypes.c_float),
                 ("d2h_ms", ctypes.c_float), ("kernel_launches", ctypes.c_uint32), ("prep_ms", ctypes.c_float),
-                ("exact_fallbacks", ctypes.c_uint32), ("reserved", ctypes.c_uint32)]
+                ("exact_fallbacks", ctypes.c_uint32), ("verify_ms", ctypes.c_float)]
+
+
+class VerifyOpts(ctypes.Structure):
+    _fields_ = [("focal", ctypes.c_double), ("cx", ctypes.c_double), ("cy", ctypes.c_double), ("n_hyp", ctypes.c_uint32), ("shared", ctypes.c_uint32)]
+
+
+MODEL_ESSENTIAL, MODEL_HOMOGRAPHY = 0, 1
+VERIFY_DTYPE = [("best", "<u4"), ("n_inliers", "<u4"), ("median", "<f4"), ("sigma", "<f4")]
 
 
 class MultiTiming(ctypes.Structure):
@@ -54,7 +62,7 @@ SYMBOLS = [
     "eacham_gpu_flush_l2",
     "eacham_gpu_create_multi", "eacham_gpu_destroy_multi", "eacham_gpu_multi_device_count", "eacham_gpu_multi_set_descriptors",
     "eacham_gpu_multi_clear", "eacham_gpu_multi_commit", "eacham_gpu_multi_match_pairs", "eacham_gpu_multi_last_timing",
-    "eacham_gpu_host_alloc", "eacham_gpu_host_free", "eacham_gpu_debug_pair_knn2",
+    "eacham_gpu_host_alloc", "eacham_gpu_host_free", "eacham_gpu_debug_pair_knn2", "eacham_gpu_set_keypoints", "eacham_gpu_verify_pairs",
 ]
 
 _lib = None
@@ -100,6 +108,8 @@ def load() -> ctypes.CDLL:
     lib.eacham_gpu_last_timing.argtypes = [vp, P(Timing)]
     lib.eacham_gpu_flush_l2.argtypes = [vp, sz]
     lib.eacham_gpu_debug_pair_knn2.argtypes = [vp, u32, u32, P(MatchOpts), vp, vp, vp, vp]
+    lib.eacham_gpu_set_keypoints.argtypes = [vp, u32, vp, u32, sz]
+    lib.eacham_gpu_verify_pairs.argtypes = [vp, i32, vp, P(VerifyOpts), vp, vp, vp]
     lib.eacham_gpu_create_multi.argtypes = [P(ctypes.c_int32), u32, P(Config), P(vp)]
     lib.eacham_gpu_destroy_multi.argtypes = [vp]
     lib.eacham_gpu_destroy_multi.restype = None

@@ -22,6 +22,7 @@
 #include "orb_kernels.cuh"
 #include "tc_match_kernels.cuh"
 #include "tc_orb_kernels.cuh"
+#include "verify_kernels.cuh"
 
 namespace {
 
@@ -128,6 +129,17 @@ struct eacham_gpu_handle {
 
     cudaEvent_t ev[8] = {};
     eacham_gpu_timing timing = {};
+
+    // ---- geometric verification (verify_kernels.cuh) ----
+    std::vector<std::vector<float>> kp_host;  // per image: x, y interleaved
+    bool kp_dirty = true;
+    DevBuf<float2> d_kp;
+    DevBuf<unsigned long long> d_kp_offset;
+    DevBuf<double> d_hyps;
+    DevBuf<eacham_verify_result> d_vres;
+    DevBuf<float> d_vmed;
+    DevBuf<uint8_t> d_vmask;
+    uint32_t last_max_first = 0, last_max_second = 0;
 
     // ---- the per-call Match() route on the tensor-core engines (match_single.cuh) ----
     struct CacheEntry {                       // one image's descriptors, resident on the device across calls
@@ -266,7 +278,8 @@ void eacham_gpu_destroy(eacham_gpu_handle* h) {
         DeviceGuard g(h->device);
         if (h->stream) cudaStreamSynchronize(h->stream);
         h->tc_arena.release(); h->d_images_tc.release(); h->d_block_start.release(); h->tc_scratch.release();
-        h->arena.release(); h->d_images.release(); h->d_pairs.release(); h->d_order.release(); h->d_dbg_idx.release(); h->d_dbg_dist.release(); h->d_results.release(); h->d_matches.release();
+        h->arena.release(); h->d_images.release(); h->d_pairs.release(); h->d_order.release(); h->d_dbg_idx.release(); h->d_dbg_dist.release();
+        h->d_kp.release(); h->d_kp_offset.release(); h->d_hyps.release(); h->d_vres.release(); h->d_vmed.release(); h->d_vmask.release(); h->d_results.release(); h->d_matches.release();
         h->d_counter.release(); h->d_cursor.release(); h->d_q.release(); h->d_t.release(); h->d_partial.release();
         h->d_idx.release(); h->d_dist.release(); h->d_match.release(); h->d_match2.release(); h->d_flush.release();
         if (h->staging) cudaFreeHost(h->staging);
@@ -320,6 +333,7 @@ int eacham_gpu_clear(eacham_gpu_handle* h) {
     h->images.clear();
     h->staging_used = 0; h->staging_waste = 0; h->committed = false; h->any_data = false; h->arena_bytes = 0;
     h->max_rows[0] = h->max_rows[1] = 0;
+    h->kp_host.clear(); h->kp_dirty = true;
     return EACHAM_OK;
 }
 
@@ -720,6 +734,7 @@ int launch_pairs(eacham_gpu_handle* h, const eacham_pair_t* pairs, size_t n_pair
     CUDA_TRY(cudaEventElapsedTime(&h->timing.pairs_h2d_ms, h->ev[2], h->ev[3]));
     CUDA_TRY(cudaEventElapsedTime(&h->timing.kernel_ms, h->ev[4], h->ev[5]));
     h->last_n_pairs = n_pairs;           // only a completed batch can be fetched
+    h->last_max_first = max_first; h->last_max_second = max_second;
     return EACHAM_OK;
 }
 
@@ -805,6 +820,83 @@ extern "C" int eacham_gpu_debug_pair_knn2(eacham_gpu_handle* h, uint32_t first, 
     CUDA_TRY(cudaMemcpyAsync(idx21, h->d_dbg_idx.p + 2 * n1, 2 * n2 * sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream));
     CUDA_TRY(cudaMemcpyAsync(dist21, h->d_dbg_dist.p + 2 * n1, 2 * n2 * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
     CUDA_TRY(cudaStreamSynchronize(h->stream));
+    return EACHAM_OK;
+}
+
+extern "C" int eacham_gpu_set_keypoints(eacham_gpu_handle* h, uint32_t image_id, const float* xy, uint32_t rows, size_t row_stride_bytes) {
+    if (!h) return fail(EACHAM_ERR_INVALID_ARG, "null handle");
+    if (rows > 0 && !xy) return fail(EACHAM_ERR_INVALID_ARG, "null keypoint pointer for image %u", image_id);
+    if (rows > 0 && row_stride_bytes < 2 * sizeof(float)) return fail(EACHAM_ERR_INVALID_ARG, "keypoint row stride %zu < 8", row_stride_bytes);
+    if (image_id > (1u << 26)) return fail(EACHAM_ERR_INVALID_ARG, "image id %u out of range", image_id);
+    std::lock_guard<std::mutex> lk(h->mu);
+    if (image_id >= h->kp_host.size()) h->kp_host.resize((size_t)image_id + 1);
+    std::vector<float>& v = h->kp_host[image_id];
+    v.resize((size_t)rows * 2);
+    for (uint32_t r = 0; r < rows; ++r) memcpy(&v[2 * (size_t)r], reinterpret_cast<const uint8_t*>(xy) + (size_t)r * row_stride_bytes, 2 * sizeof(float));
+    h->kp_dirty = true;
+    return EACHAM_OK;
+}
+
+extern "C" int eacham_gpu_verify_pairs(eacham_gpu_handle* h, int model, const double* hyps, const eacham_verify_opts* opts, eacham_verify_result* res,
+                                       float* medians, uint8_t* mask) {
+    using namespace eacham;
+    if (!h || !hyps || !opts || !res) return fail(EACHAM_ERR_INVALID_ARG, "null argument");
+    if (model != EACHAM_MODEL_ESSENTIAL && model != EACHAM_MODEL_HOMOGRAPHY) return fail(EACHAM_ERR_INVALID_ARG, "unknown model %d", model);
+    if (opts->n_hyp == 0) return fail(EACHAM_ERR_INVALID_ARG, "need at least one hypothesis");
+    if (model == EACHAM_MODEL_ESSENTIAL && !(opts->focal > 0.0)) return fail(EACHAM_ERR_INVALID_ARG, "focal length must be positive");
+    std::lock_guard<std::mutex> lk(h->mu);
+    DeviceGuard g(h->device);
+    const size_t n_pairs = h->last_n_pairs;
+    if (n_pairs == 0) return fail(EACHAM_ERR_NOT_COMMITTED, "no completed match_pairs batch on this handle to verify");
+    const uint32_t max_matches = std::min(h->last_max_first, h->last_max_second);       // a pair has at most min(rows) mutual matches
+    if (max_matches > verify::kMaxMatches) return fail(EACHAM_ERR_TOO_LARGE, "up to %u matches per pair are supported for verification", verify::kMaxMatches);
+    int rc;
+    if (h->kp_dirty) {                                   // keypoint table: every image of the arena needs one row per descriptor
+        std::vector<unsigned long long> off(h->images.size() + 1, 0);
+        size_t total = 0;
+        for (size_t i = 0; i < h->images.size(); ++i) {
+            off[i] = total;
+            const size_t have = i < h->kp_host.size() ? h->kp_host[i].size() / 2 : 0;
+            if (h->images[i].present && have != h->images[i].rows)
+                return fail(EACHAM_ERR_INVALID_ARG, "image %zu has %u descriptors but %zu keypoints", i, h->images[i].rows, have);
+            total += have;
+        }
+        off[h->images.size()] = total;
+        if ((rc = h->d_kp.ensure(std::max(total, (size_t)1))) || (rc = h->d_kp_offset.ensure(off.size()))) return rc;
+        std::vector<float> flat(2 * std::max(total, (size_t)1));
+        for (size_t i = 0; i < h->images.size() && i < h->kp_host.size(); ++i)
+            if (!h->kp_host[i].empty()) memcpy(&flat[2 * off[i]], h->kp_host[i].data(), h->kp_host[i].size() * sizeof(float));
+        CUDA_TRY(cudaMemcpyAsync(h->d_kp.p, flat.data(), 2 * total * sizeof(float), cudaMemcpyHostToDevice, h->stream));
+        CUDA_TRY(cudaMemcpyAsync(h->d_kp_offset.p, off.data(), off.size() * sizeof(off[0]), cudaMemcpyHostToDevice, h->stream));
+        CUDA_TRY(cudaStreamSynchronize(h->stream));
+        h->kp_dirty = false;
+    }
+    const size_t n_h = (size_t)opts->n_hyp * (opts->shared ? 1 : n_pairs) * 9;
+    if ((rc = h->d_hyps.ensure(n_h)) || (rc = h->d_vres.ensure(n_pairs))) return rc;
+    if (medians && (rc = h->d_vmed.ensure(n_pairs * opts->n_hyp))) return rc;
+    if (mask && (rc = h->d_vmask.ensure(std::max((size_t)h->last_total, (size_t)1)))) return rc;
+    CUDA_TRY(cudaMemcpyAsync(h->d_hyps.p, hyps, n_h * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    verify::Params p;
+    p.pairs = h->d_pairs.p; p.results = h->d_results.p; p.matches = h->d_matches.p; p.keypoints = h->d_kp.p; p.kp_offset = h->d_kp_offset.p;
+    p.hyps = h->d_hyps.p; p.n_pairs = (uint32_t)n_pairs; p.n_hyp = opts->n_hyp; p.shared = opts->shared ? 1u : 0u; p.model = (uint32_t)model;
+    p.focal = opts->focal; p.cx = opts->cx; p.cy = opts->cy;
+    p.out = h->d_vres.p; p.medians = medians ? h->d_vmed.p : nullptr; p.mask = mask ? h->d_vmask.p : nullptr;
+    uint32_t cap = 64;
+    while (cap < max_matches) cap <<= 1;
+    p.cap = cap;
+    const size_t smem = (size_t)cap * (sizeof(float4) + 2 * sizeof(float));
+    CUDA_TRY(cudaFuncSetAttribute(verify::verify_pairs_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const unsigned per_sm = (unsigned)std::max<size_t>(1, std::min<size_t>(8, (200 * 1024) / std::max(smem, (size_t)1024)));
+    const unsigned grid = (unsigned)std::min<size_t>(n_pairs, (size_t)h->sm_count * per_sm);
+    CUDA_TRY(cudaEventRecord(h->ev[0], h->stream));
+    verify::verify_pairs_kernel<<<grid, verify::kThreads, smem, h->stream>>>(p);
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaEventRecord(h->ev[1], h->stream));
+    CUDA_TRY(cudaMemcpyAsync(res, h->d_vres.p, n_pairs * sizeof(eacham_verify_result), cudaMemcpyDeviceToHost, h->stream));
+    if (medians) CUDA_TRY(cudaMemcpyAsync(medians, h->d_vmed.p, n_pairs * opts->n_hyp * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
+    if (mask && h->last_total) CUDA_TRY(cudaMemcpyAsync(mask, h->d_vmask.p, (size_t)h->last_total, cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(cudaStreamSynchronize(h->stream));
+    CUDA_TRY(cudaEventElapsedTime(&h->timing.verify_ms, h->ev[0], h->ev[1]));
     return EACHAM_OK;
 }
 

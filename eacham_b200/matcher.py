@@ -169,6 +169,7 @@ class FeatureMatcherGpu:
         """C-ABI call with host buffers: returns (results record array [n_pairs], matches record array [used])."""
         arr = self._pairs_array(pairs)
         n = arr.shape[0]
+        self._last_n = n
         res = np.zeros(n, dtype=L.RESULT_DTYPE)
         opts = self._opts(emit_all)
         used = ctypes.c_size_t()
@@ -230,7 +231,34 @@ class FeatureMatcherGpu:
         t = L.Timing()
         L.check(self._lib.eacham_gpu_last_timing(self._h, ctypes.byref(t)))
         return dict(upload_ms=t.upload_ms, pairs_h2d_ms=t.pairs_h2d_ms, kernel_ms=t.kernel_ms, d2h_ms=t.d2h_ms,
-                    kernel_launches=int(t.kernel_launches), prep_ms=t.prep_ms, exact_fallbacks=int(t.exact_fallbacks))
+                    kernel_launches=int(t.kernel_launches), prep_ms=t.prep_ms, exact_fallbacks=int(t.exact_fallbacks), verify_ms=t.verify_ms)
+
+    # -- geometric verification of the last batch ------------------------------------------------
+    def SetKeypoints(self, image_id: int, xy: np.ndarray) -> None:
+        """xy[rows, 2] float32: keypoint r belongs to descriptor row r of the image."""
+        xy = np.ascontiguousarray(xy, dtype=np.float32).reshape(-1, 2)
+        L.check(self._lib.eacham_gpu_set_keypoints(self._h, image_id, xy.ctypes.data_as(ctypes.c_void_p), xy.shape[0], 8))
+
+    def VerifyPairs(self, model: int, hyps: np.ndarray, focal: float = 1.0, cx: float = 0.0, cy: float = 0.0, want_medians: bool = False,
+                    want_mask: bool = False):
+        """Scores hypotheses for every pair of the last MatchPairs* batch (eacham_gpu_verify_pairs). hyps: [n_hyp, 3, 3] shared by all
+        pairs, or [n_pairs, n_hyp, 3, 3]. Returns (results record array, medians or None, mask or None)."""
+        hyps = np.ascontiguousarray(hyps, dtype=np.float64)
+        shared = hyps.ndim == 3
+        n_hyp = hyps.shape[0] if shared else hyps.shape[1]
+        n = self._last_n
+        if not shared and hyps.shape[0] != n:
+            raise ValueError("per-pair hypotheses must have one block per pair of the last batch")
+        opts = L.VerifyOpts(focal=float(focal), cx=float(cx), cy=float(cy), n_hyp=int(n_hyp), shared=1 if shared else 0)
+        res = np.zeros(n, dtype=L.VERIFY_DTYPE)
+        med = np.zeros((n, n_hyp), np.float32) if want_medians else None
+        _, _, _, n_matches = self.device_results()
+        mask = np.zeros(max(n_matches, 1), np.uint8) if want_mask else None
+        L.check(self._lib.eacham_gpu_verify_pairs(self._h, model, hyps.ctypes.data_as(ctypes.c_void_p), ctypes.byref(opts),
+                                                  res.ctypes.data_as(ctypes.c_void_p),
+                                                  med.ctypes.data_as(ctypes.c_void_p) if want_medians else None,
+                                                  mask.ctypes.data_as(ctypes.c_void_p) if want_mask else None))
+        return res, med, (mask[:n_matches] if want_mask else None)
 
     def DebugPairKnn2(self, first: int, second: int):
         """(idx12[n1,2], dist12[n1,2], idx21[n2,2], dist21[n2,2]): the kNN(k=2) the batched tensor-core SIFT path's ratio test saw

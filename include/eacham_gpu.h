@@ -118,7 +118,7 @@ typedef struct eacham_gpu_timing {
     uint32_t kernel_launches; /* kernels launched by the last match_pairs                                     */
     float prep_ms;      /* tensor-core operand copy of the arena (bf16 / one e4m3 per bit), built once after a commit */
     uint32_t exact_fallbacks; /* F32X128 tensor engine: queries of the last batch re-done by the exact FP32 scan (see below) */
-    uint32_t reserved;
+    float verify_ms;    /* eacham_gpu_verify_pairs: the scoring kernel                                              */
 } eacham_gpu_timing;
 
 EACHAM_API int eacham_gpu_abi_version(void);
@@ -220,6 +220,39 @@ EACHAM_API int eacham_gpu_multi_last_timing(eacham_gpu_multi* m, eacham_gpu_mult
 /* Page-locked host memory usable by every device (result buffers copied at full PCIe rate); NULL on failure. */
 EACHAM_API void* eacham_gpu_host_alloc(size_t bytes);
 EACHAM_API void eacham_gpu_host_free(void* p);
+
+/* ---- next on the path: geometric verification of the matched pairs ------------------------------------
+ * ReconstructionManager::RecoverPoseTwoView (modules/sfm/reconstruction/ReconstructionManager.cpp:47-86) runs
+ * cv::findEssentialMat(LMEDS) and cv::findHomography(LMEDS) on every factor's matched keypoints and counts each model's inliers;
+ * FindBestPair does so twice per factor (modules/sfm/utils/Utils.h:24-68). Both are hypothesise-and-score loops. This call does
+ * the scoring -- residual of every match under every hypothesis, least median of squares, sigma and inlier mask exactly as
+ * OpenCV's LMedS registrator defines them -- for ALL pairs of the last eacham_gpu_match_pairs* batch on this handle, straight from
+ * the device-resident match lists and the keypoints set below. Hypotheses come from the caller (minimal solvers stay on the host). */
+typedef enum eacham_model {
+    EACHAM_MODEL_ESSENTIAL = 0,   /* 3x3 E on normalised coordinates ((u - cx) / focal, (v - cy) / focal): Sampson-type error of five-point.cpp, double */
+    EACHAM_MODEL_HOMOGRAPHY = 1   /* 3x3 H on pixel coordinates: forward transfer error of fundam.cpp, float                                           */
+} eacham_model;
+
+typedef struct eacham_verify_opts {
+    double focal, cx, cy;     /* ESSENTIAL: as cv::findEssentialMat(points1, points2, focal, pp, ...) (ReconstructionManager.cpp:58-61) */
+    uint32_t n_hyp;           /* hypotheses per pair                                                                                     */
+    uint32_t shared;          /* 1 = one set of n_hyp hypotheses for all pairs ([n_hyp][9]); 0 = per pair ([n_pairs][n_hyp][9])          */
+} eacham_verify_opts;
+
+typedef struct eacham_verify_result {
+    uint32_t best;        /* index of the hypothesis with the least median (first on ties)                          */
+    uint32_t n_inliers;   /* matches with err <= sigma^2 under it: the reference's E_Inliers / H_Inliers              */
+    float median;         /* its median squared error                                                               */
+    float sigma;          /* 2.5 * 1.4826 * (1 + 5 / (n - modelPoints)) * sqrt(median), at least 0.001                */
+} eacham_verify_result;
+
+/* Keypoints of one image: rows x (x, y) float32, row r belongs to descriptor row r (Node::GetKeyPoint, ReconstructionManager.cpp:15-30). */
+EACHAM_API int eacham_gpu_set_keypoints(eacham_gpu_handle* h, uint32_t image_id, const float* xy, uint32_t rows, size_t row_stride_bytes);
+/* hyps: row-major 3x3 doubles. res[n_pairs] (pairs of the last batch, input order). medians ([n_pairs][n_hyp]) and mask (one byte per
+ * entry of the last batch's match buffer, 1 = inlier of the pair's best hypothesis) may be NULL. Pairs with no more matches than
+ * the model's minimal sample (5 / 4) get zeros. At most 8192 matches per pair. */
+EACHAM_API int eacham_gpu_verify_pairs(eacham_gpu_handle* h, int model, const double* hyps, const eacham_verify_opts* opts,
+                                       eacham_verify_result* res, float* medians, uint8_t* mask);
 
 EACHAM_API int eacham_gpu_last_timing(eacham_gpu_handle* h, eacham_gpu_timing* t);
 /* Write `bytes` of device memory (L2 flush between timed benchmark iterations). */
