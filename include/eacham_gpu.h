@@ -161,6 +161,19 @@ EACHAM_API int eacham_gpu_match(eacham_gpu_handle* h, int kind, const void* quer
 EACHAM_API int eacham_gpu_knn2(eacham_gpu_handle* h, int kind, const void* query, uint32_t q_rows, size_t q_stride_bytes,
                     const void* train, uint32_t t_rows, size_t t_stride_bytes, int32_t* idx, float* dist);
 
+/* Exactness of the batched path.
+ * ORB256: bit-exact on every engine -- indices, counts, flags and match lists equal cv::BFMatcher(NORM_HAMMING).knnMatch(k=2) + the
+ *   reference's ratio / gate / mutual code. The tensor-core engines carry no indices in their hot loop and rely on a match being a
+ *   strict unique minimum (true for ratio <= 1); a call with ratio > 1 runs on the packed-key XOR+POPC kernels instead.
+ * F32X128: candidates are scored as a bf16 GEMM (exact for integer-valued rows, which is what cv::SIFT emits) and re-ranked in exact
+ *   FP32. With |score - |a-b|^2/2| <= E for every train row, where
+ *       E = delta (2 d1 + delta) / 2 + 2^-15 d1^2 / 2 + 2^-16 (|a|^2 + max|b|^2) / 2,   delta = 2^-9 (|a| + max|b|)
+ *   (first and last term 0 when both images are bf16-exact), the reference's ratio lies in [d0/d1, d0/sqrt(d1^2 - 4E)]. Only if that
+ *   interval straddles `ratio` (or the best itself could be a non-candidate) is the query re-done by an exact FP32 scan over all train
+ *   rows (eacham_gpu_timing.exact_fallbacks counts them). The returned match sets are therefore the exact matcher's for ANY float
+ *   input; epsilon (relative width 3e-5 of the ratio for integer-valued rows, about 1.4 % for unit-norm floats) only decides how
+ *   many queries take the slow path. Distances: eacham_gpu_knn2 / eacham_gpu_debug_pair_knn2. */
+
 /* The batched path: for every unordered pair both directions + ratio + gates + mutual filter on the GPU
  * (apps/sfm/main.cpp:84-147). res has n_pairs entries; matches of pair p are buf[res[p].offset .. +count),
  * sorted by query index, query = row in image `first`, train = row in image `second`.
