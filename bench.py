@@ -195,7 +195,7 @@ def workload_config(name, n_images, n_pairs, gpus):
                         + (f"sliding window (each frame vs next {win}) = {n_pairs} unordered pairs" if win else f"exhaustive {n_pairs} unordered pairs")
                         + ", ratio 0.8 + cross-check, gates 30/30",
             "images": n_images, "descriptors_per_image": n_desc, "pairs": n_pairs, "pairs_per_gpu": n_pairs // max(gpus, 1),
-            "parallelism": f"fixed pair list sharded rank::{gpus} (strong scaling), arena replicated by one NCCL broadcast" if gpus > 1 else "single GPU",
+            "parallelism": f"fixed pair list sharded over {gpus} GPUs in whole 16x16 image blocks (strong scaling), arena replicated by one NCCL broadcast" if gpus > 1 else "single GPU",
             "l2": "flushed between timed steps (256 MiB device memset outside the event-timed region); per-step CUDA events summed",
             "orb_engine": "tensor (tcgen05 kind::f8f6f4, F16 accumulators, packed epilogue)" if kind == "orb" else None}
 
@@ -537,7 +537,7 @@ def run_multi_gpu(env, args):
     value = n_pairs * args.steps / (total_ms * 1e-3)
 
     # parity of the GATHERED result on rank 0: shards travel GPU -> GPU over NVLink, pair order restored, CPU-checked sample
-    got = D.gather_results_device(m, n_pairs, dst=0)
+    got = D.gather_results_device(m, all_pairs, dst=0)
     cpu = None
     if env.rank == 0:
         res_all, buf_all = got

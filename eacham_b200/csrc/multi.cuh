@@ -1,7 +1,7 @@
 // multi.cuh -- one process, several B200s of one NVSwitch box, behind the C ABI (include/eacham_gpu.h, eacham_gpu_multi_*).
 //
 // The pair list of /root/reference/apps/sfm/main.cpp:84-92 is a set of independent units, so the path shards with no data-path
-// exchange: every device holds the whole descriptor arena, device g matches pairs g, g + n, g + 2n, ... and copies ITS shard of
+// exchange: every device holds the whole descriptor arena, every device matches its share of the pair list (whole blocks of the image x image grid) and copies ITS shard of
 // the results over ITS PCIe link into its slice of the caller's buffers. The only collective is one broadcast of the arena:
 // devices[0] receives the staged bytes (one H2D) and ncclBroadcast (ncclCommInitAll, one stream per device, NVLink through
 // NVSwitch) replicates them. NCCL is bound at run time (dlopen of libnccl.so.2) so the single-device library has no NCCL
@@ -59,6 +59,8 @@ struct eacham_gpu_multi {
     std::mutex mu;
     // per device, reused across calls
     std::vector<std::vector<eacham_pair_t>> shard;
+    std::vector<std::vector<uint32_t>> shard_index;          // input index of every shard element
+    std::vector<uint32_t> block_rank;                        // scratch of the block-level sharding
     std::vector<eacham_pair_result_t*> res_pinned;
     std::vector<size_t> res_pinned_cap;
     eacham_gpu_multi_timing timing = {};
@@ -109,6 +111,7 @@ int eacham_gpu_create_multi(const int32_t* devices, uint32_t n_devices, const ea
         m->dev.push_back(h);
     }
     m->shard.resize(n_devices);
+    m->shard_index.resize(n_devices);
     m->res_pinned.assign(n_devices, nullptr);
     m->res_pinned_cap.assign(n_devices, 0);
     if (!(m->flags & EACHAM_CFG_MULTI_PARALLEL_H2D)) {
@@ -212,12 +215,31 @@ int eacham_gpu_multi_match_pairs(eacham_gpu_multi* m, const eacham_pair_t* pairs
     std::lock_guard<std::mutex> lk(m->mu);
     const size_t n = m->dev.size();
     const double t0 = now_ms();
-    // shard: pair k -> device k % n (equal counts +-1 and, for an exhaustive list in row-major order, an even mix of images)
+    // shard: whole 16 x 16 blocks of the image x image grid go to one device, round-robin over the occupied blocks, so that every
+    // device works through complete blocks whose ~32 images stay resident in its L2 (pair k -> device k % n would leave each device
+    // 1/n of every block and n times as many images in flight). Sparse id ranges fall back to k % n.
     for (size_t g = 0; g < n; ++g) {
-        m->shard[g].clear();
-        m->shard[g].reserve(n_pairs / n + 1);
+        m->shard[g].clear(); m->shard_index[g].clear();
+        m->shard[g].reserve(n_pairs / n + 256); m->shard_index[g].reserve(n_pairs / n + 256);
     }
-    for (size_t k = 0; k < n_pairs; ++k) m->shard[k % n].push_back(pairs[k]);
+    {
+        constexpr uint32_t kBlock = 16;
+        uint32_t max_id = 0;
+        for (size_t k = 0; k < n_pairs; ++k) max_id = std::max(max_id, std::max(pairs[k].first, pairs[k].second));
+        const size_t nb = (size_t)max_id / kBlock + 1;
+        const bool blocked = n > 1 && nb * nb <= 4 * n_pairs + 1024;
+        if (blocked) {
+            m->block_rank.assign(nb * nb, 0u);
+            for (size_t k = 0; k < n_pairs; ++k) m->block_rank[(size_t)(pairs[k].first / kBlock) * nb + pairs[k].second / kBlock] = 1u;
+            uint32_t dense = 0;
+            for (auto& b : m->block_rank) if (b) b = 1u + (dense++ % (uint32_t)n);      // 0 = empty, else device + 1
+        }
+        for (size_t k = 0; k < n_pairs; ++k) {
+            const size_t g = blocked ? m->block_rank[(size_t)(pairs[k].first / kBlock) * nb + pairs[k].second / kBlock] - 1u : k % n;
+            m->shard[g].push_back(pairs[k]);
+            m->shard_index[g].push_back((uint32_t)k);
+        }
+    }
     std::vector<size_t> total(n, 0);
     int rc = for_each_device(m, [&](size_t g) -> int {
         return eacham_gpu_match_pairs_device(m->dev[g], m->shard[g].data(), m->shard[g].size(), opts, &total[g]);
@@ -249,7 +271,7 @@ int eacham_gpu_multi_match_pairs(eacham_gpu_multi* m, const eacham_pair_t* pairs
         for (size_t i = 0; i < np; ++i) {
             eacham_pair_result_t v = src[i];
             v.offset += base[g];
-            res[i * n + g] = v;
+            res[m->shard_index[g][i]] = v;
         }
         return EACHAM_OK;
     });

@@ -83,6 +83,11 @@ class FeatureMatcherGpu:
 
     # -- lifetime ---------------------------------------------------------------------------------------
     def close(self):
+        for name in ("_pin_res", "_pin_buf"):
+            b = getattr(self, name, None)
+            if b is not None:
+                b.close()
+                setattr(self, name, None)
         if getattr(self, "_h", None):
             self._lib.eacham_gpu_destroy(self._h)
             self._h = None
@@ -165,21 +170,34 @@ class FeatureMatcherGpu:
         arr = np.ascontiguousarray(np.asarray(pairs, dtype=np.uint32).reshape(-1, 2))
         return arr
 
+    def _pinned(self, which: str, n: int, dtype):
+        """Reusable page-locked host buffer (eacham_gpu_host_alloc): D2H at full PCIe rate instead of through the driver's bounce buffers."""
+        from .multi import PinnedBuffer
+        cur = getattr(self, which, None)
+        if cur is None or cur.n < n:
+            if cur is not None:
+                cur.close()
+            cur = PinnedBuffer(self._lib, int(n * 1.25) + 1024, dtype)
+            setattr(self, which, cur)
+        return cur
+
     def MatchPairsRaw(self, pairs, emit_all: bool = False, buf: Optional[np.ndarray] = None):
-        """C-ABI call with host buffers: returns (results record array [n_pairs], matches record array [used])."""
+        """C-ABI call with host buffers: returns (results record array [n_pairs], matches record array [used]). Unless `buf` is given
+        both are views of pinned buffers owned by this object, valid until its next MatchPairsRaw / close."""
         arr = self._pairs_array(pairs)
         n = arr.shape[0]
         self._last_n = n
-        res = np.zeros(n, dtype=L.RESULT_DTYPE)
         opts = self._opts(emit_all)
         used = ctypes.c_size_t()
-        if buf is None:
-            buf = np.empty(max(n * 192, 1 << 16), dtype=L.MATCH_DTYPE)
+        res = self._pinned("_pin_res", max(n, 1), L.RESULT_DTYPE).array[:n]
+        own = buf is None
+        if own:
+            buf = self._pinned("_pin_buf", max(n * 192, 1 << 16), L.MATCH_DTYPE).array
         rc = self._lib.eacham_gpu_match_pairs(self._h, arr.ctypes.data_as(ctypes.c_void_p), n, ctypes.byref(opts),
                                               res.ctypes.data_as(ctypes.c_void_p), buf.ctypes.data_as(ctypes.c_void_p),
                                               buf.shape[0], ctypes.byref(used))
         if rc == L.ERR_BUFFER_TOO_SMALL:
-            buf = np.empty(used.value, dtype=L.MATCH_DTYPE)
+            buf = self._pinned("_pin_buf", used.value, L.MATCH_DTYPE).array if own else np.empty(used.value, dtype=L.MATCH_DTYPE)
             L.check(self._lib.eacham_gpu_fetch_results(self._h, res.ctypes.data_as(ctypes.c_void_p), n,
                                                        buf.ctypes.data_as(ctypes.c_void_p), buf.shape[0], ctypes.byref(used)))
         else:

@@ -202,8 +202,8 @@ EACHAM_API int eacham_gpu_fetch_results(eacham_gpu_handle* h, eacham_pair_result
 EACHAM_API int eacham_gpu_device_results(eacham_gpu_handle* h, void** results, void** matches, size_t* n_pairs, size_t* n_matches);
 
 /* ---- several devices of one box in ONE process (the reference is a single-process C++ app, apps/sfm/main.cpp) ----------
- * The pair list shards with no data-path exchange: every device holds the whole arena, device g matches pairs
- * g, g + n, g + 2n, ... and copies its own shard of the results into its slice of the caller's buffers over its own PCIe link.
+ * The pair list shards with no data-path exchange: every device holds the whole arena, matches its share of
+ * the pair list (whole 16 x 16 blocks of the image x image grid, so that its working set stays in L2) and copies its own shard of the results into its slice of the caller's buffers over its own PCIe link.
  * eacham_gpu_multi_commit = one H2D copy to devices[0] + ONE ncclBroadcast of the arena over NVLink (ncclCommInitAll, one stream
  * per device; libnccl.so.2 is bound at run time). Results are exactly those of the single-device calls, in input order:
  * buf holds device 0's matches, then device 1's, ...; res[k].offset indexes into buf. */

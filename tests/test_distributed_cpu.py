@@ -23,7 +23,7 @@ def _worker(rank, world, port, n_images, out_path):
     imgs = synth.orb_image_set(n_images, 300, seed=21, pool=330)
     pairs = synth.exhaustive_pairs(n_images)
     mine = D.shard_pairs(pairs, rank, world)
-    assert len(mine) == D.shard_sizes(len(pairs), world)[rank]
+    assert len(mine) == D.shard_sizes(pairs, world)[rank]
     res = np.zeros(len(mine), dtype=L.RESULT_DTYPE); chunks = []; off = 0
     for k, (i, j) in enumerate(mine.tolist()):
         r = O.c_match_pair(imgs[i], imgs[j])
@@ -32,7 +32,7 @@ def _worker(rank, world, port, n_images, out_path):
         rec = np.zeros(len(m), dtype=L.MATCH_DTYPE); rec["query"] = m[:, 0]; rec["train"] = m[:, 1]
         chunks.append(rec); off += len(m)
     buf = np.concatenate(chunks) if chunks else np.zeros(0, L.MATCH_DTYPE)
-    got = D.gather_results(res, buf, len(pairs), dst=0)
+    got = D.gather_results(res, buf, pairs, dst=0)
     if rank == 0:
         full_res, full_buf = got
         ok = True
@@ -60,8 +60,16 @@ def test_shard_gather_roundtrip_gloo(tmp_path):
 
 def test_shard_unshard_identity():
     from eacham_b200 import distributed as D
-    pairs = np.arange(2 * 37, dtype=np.uint32).reshape(37, 2)
-    for world in (1, 2, 3, 4, 8):
-        parts = [D.shard_pairs(pairs, r, world) for r in range(world)]
-        assert sum(len(p) for p in parts) == 37 and [len(p) for p in parts] == D.shard_sizes(37, world)
-        assert np.array_equal(D.unshard(parts, 37), pairs)
+    from eacham_b200 import synth
+    for pairs in (np.arange(2 * 37, dtype=np.uint32).reshape(37, 2), synth.exhaustive_pairs(70), synth.window_pairs(200, 20)):
+        for world in (1, 2, 3, 4, 8):
+            parts = [D.shard_pairs(pairs, r, world) for r in range(world)]
+            assert sum(len(p) for p in parts) == len(pairs) and [len(p) for p in parts] == D.shard_sizes(pairs, world)
+            assert np.array_equal(D.unshard(parts, pairs), pairs)
+            owner = D.shard_owner(pairs, world)
+            blocks = (pairs[:, 0].astype(np.int64) // 16) * 100000 + pairs[:, 1] // 16
+            for b in np.unique(blocks):                       # a block of the image grid is never split between ranks
+                assert len(set(owner[blocks == b].tolist())) == 1
+    big = synth.exhaustive_pairs(2000)                        # BASELINE config 5: shards within 0.2 % of each other
+    sizes = D.shard_sizes(big, 8)
+    assert max(sizes) - min(sizes) < 0.002 * len(big)

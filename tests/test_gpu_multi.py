@@ -29,7 +29,7 @@ def _worker(rank, world, port, out_path):
     m = eacham_b200.FeatureMatcherGpu(0.8, device=rank)
     D.upload_and_broadcast(m, imgs, src=0)
     m.MatchPairsDevice(D.shard_pairs(pairs, rank, world))
-    got = D.gather_results_device(m, len(pairs), dst=0)
+    got = D.gather_results_device(m, pairs, dst=0)
     if rank == 0:
         res, buf = got
         m.Upload(imgs)
