@@ -215,7 +215,7 @@ int eacham_gpu_multi_match_pairs(eacham_gpu_multi* m, const eacham_pair_t* pairs
     std::lock_guard<std::mutex> lk(m->mu);
     const size_t n = m->dev.size();
     const double t0 = now_ms();
-    // shard: whole 16 x 16 blocks of the image x image grid go to one device, round-robin over the occupied blocks, so that every
+    // shard: whole 16 x 16 blocks of the image x image grid go to one device (largest block first, each to the device with the least pairs so far), so that every
     // device works through complete blocks whose ~32 images stay resident in its L2 (pair k -> device k % n would leave each device
     // 1/n of every block and n times as many images in flight). Sparse id ranges fall back to k % n.
     for (size_t g = 0; g < n; ++g) {
@@ -223,16 +223,32 @@ int eacham_gpu_multi_match_pairs(eacham_gpu_multi* m, const eacham_pair_t* pairs
         m->shard[g].reserve(n_pairs / n + 256); m->shard_index[g].reserve(n_pairs / n + 256);
     }
     {
-        constexpr uint32_t kBlock = 16;
+        uint32_t kBlock = 16;
         uint32_t max_id = 0;
         for (size_t k = 0; k < n_pairs; ++k) max_id = std::max(max_id, std::max(pairs[k].first, pairs[k].second));
-        const size_t nb = (size_t)max_id / kBlock + 1;
-        const bool blocked = n > 1 && nb * nb <= 4 * n_pairs + 1024;
-        if (blocked) {
+        size_t nb = (size_t)max_id / kBlock + 1;
+        bool blocked = n > 1 && nb * nb <= 4 * n_pairs + 1024;
+        while (blocked) {                                  // small sets: finer blocks until there are enough of them to balance
             m->block_rank.assign(nb * nb, 0u);
-            for (size_t k = 0; k < n_pairs; ++k) m->block_rank[(size_t)(pairs[k].first / kBlock) * nb + pairs[k].second / kBlock] = 1u;
-            uint32_t dense = 0;
-            for (auto& b : m->block_rank) if (b) b = 1u + (dense++ % (uint32_t)n);      // 0 = empty, else device + 1
+            for (size_t k = 0; k < n_pairs; ++k) ++m->block_rank[(size_t)(pairs[k].first / kBlock) * nb + pairs[k].second / kBlock];
+            size_t occupied = 0;
+            for (uint32_t c : m->block_rank) occupied += c != 0;
+            if (kBlock == 1 || occupied >= 8 * n) break;
+            kBlock /= 2;
+            nb = (size_t)max_id / kBlock + 1;
+            blocked = nb * nb <= 4 * n_pairs + 1024;
+        }
+        if (blocked) {
+            // blocks differ in size (diagonal blocks, window lists): largest first, each to the device with the least pairs so far
+            std::vector<uint32_t> ids;
+            for (uint32_t b = 0; b < m->block_rank.size(); ++b) if (m->block_rank[b]) ids.push_back(b);
+            std::stable_sort(ids.begin(), ids.end(), [&](uint32_t a, uint32_t b) { return m->block_rank[a] > m->block_rank[b]; });
+            std::vector<size_t> load(n, 0);
+            for (uint32_t b : ids) {
+                const size_t g = (size_t)(std::min_element(load.begin(), load.end()) - load.begin());
+                load[g] += m->block_rank[b];
+                m->block_rank[b] = 1u + (uint32_t)g;       // from here on: 0 = empty, else device + 1
+            }
         }
         for (size_t k = 0; k < n_pairs; ++k) {
             const size_t g = blocked ? m->block_rank[(size_t)(pairs[k].first / kBlock) * nb + pairs[k].second / kBlock] - 1u : k % n;

@@ -13,7 +13,7 @@ def _free_port():
     s = socket.socket(); s.bind(("127.0.0.1", 0)); p = s.getsockname()[1]; s.close(); return p
 
 
-def _worker(rank, world, port, out_path):
+def _worker(rank, world, port, out_path, n_images=9):
     import sys
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     sys.path.insert(0, root)
@@ -24,8 +24,8 @@ def _worker(rank, world, port, out_path):
     os.environ["MASTER_ADDR"] = "127.0.0.1"; os.environ["MASTER_PORT"] = str(port)
     torch.cuda.set_device(rank)
     dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device(f"cuda:{rank}"))
-    imgs = synth.orb_image_set(9, 1500, seed=31, pool=2500) if rank == 0 else None
-    pairs = synth.exhaustive_pairs(9)
+    imgs = synth.orb_image_set(n_images, 1500, seed=31, pool=2500) if rank == 0 else None
+    pairs = synth.exhaustive_pairs(n_images)
     m = eacham_b200.FeatureMatcherGpu(0.8, device=rank)
     D.upload_and_broadcast(m, imgs, src=0)
     m.MatchPairsDevice(D.shard_pairs(pairs, rank, world))
@@ -54,3 +54,15 @@ def test_sharded_equals_single_gpu(tmp_path):
     mp.spawn(_worker, args=(2, _free_port(), out), nprocs=2, join=True)
     ok, n = np.load(out).tolist()
     assert ok == 1 and n > 0
+
+
+def test_sharded_with_an_empty_shard(tmp_path):
+    """Two images = one pair: one of the two ranks has nothing to match; broadcast and gather must still work."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs >= 2 GPUs")
+    import torch.multiprocessing as mp
+    out = str(tmp_path / "ok1.npy")
+    mp.spawn(_worker, args=(2, _free_port(), out, 2), nprocs=2, join=True)
+    ok, n = np.load(out).tolist()
+    assert ok == 1
