@@ -162,9 +162,10 @@ __global__ void __launch_bounds__(256) tc_prep_all_kernel(const uint8_t* __restr
 // The fused SIFT pair kernel.
 //
 // One persistent CTA per image pair (static round-robin over the pair list). 576 threads:
-//   warp 0    producer: 1-D bulk copies (TMA engine) of pre-tiled bf16 blocks, mbarrier pipeline
-//   warp 1    MMA issuer: one thread issues tcgen05.mma (M=128, N=128, K=16) x 9 k-steps x 2 row halves per tile
-//   warps 2-17 epilogue: tcgen05.ld -> packed-key top-2 for rows (registers) and columns (REDUX + smem slots)
+//   warps 0-15 epilogue: tcgen05.ld -> packed-key top-2 for rows (registers) and columns (REDUX + smem slots)
+//   warp 16   producer: 1-D bulk copies (TMA engine) of pre-tiled bf16 blocks, mbarrier pipeline
+//   warp 17   MMA issuer: one elected thread issues tcgen05.mma (M=128, N=128, K=16) x 9 k-steps x 2 row halves per tile
+// (the single-thread roles sit in the highest warps: the scheduler favours higher warp ids and they must never starve)
 // A block of 256 rows of the first image stays in shared memory while the second image streams through in
 // 128-column tiles (3 stages). Accumulators: 2 stages x 2 halves x 128 fp32 columns = all 512 TMEM columns, so the
 // tensor core fills stage s+1 while the epilogue drains stage s.
@@ -252,7 +253,7 @@ __device__ __forceinline__ float exact_l2(const float4 a4, const float* __restri
 
 // kNN(k=2) of one query row by an exact scan over ALL train rows (OpenCV order: ascending distance, ties to the lower index),
 // warp-cooperative with the same arithmetic as the re-rank (exact_l2). The slow path of rerank_ratio_checked.
-__device__ __forceinline__ void exact_scan_top2(const float4 a4, const float* __restrict__ tbase, uint32_t n_train, int lane,
+__device__ __noinline__ void exact_scan_top2(const float4 a4, const float* __restrict__ tbase, uint32_t n_train, int lane,
                                                 float& d0, float& d1, uint32_t& j0, uint32_t& j1) {
     d0 = d1 = __int_as_float(0x7f800000);
     j0 = j1 = EACHAM_NONE;
@@ -496,13 +497,13 @@ __global__ void __launch_bounds__(kThreadsTc, 1) tc_match_pairs_kernel(const Pai
         for (int s = 0; s < kAccStages; ++s) { tc::mbar_init(&S.acc_full[s], 1); tc::mbar_init(&S.acc_empty[s], kEpiWarps); }
         tc::fence_barrier_init();
     }
-    if (warp == 1) tc::tmem_alloc(&S.tmem_slot, 512);
+    if (warp == kEpiWarps + 1) tc::tmem_alloc(&S.tmem_slot, 512);
     tc::tc_fence_before();
     __syncthreads();
     tc::tc_fence_after();
     const uint32_t tmem = S.tmem_slot;
 
-    if (warp == 0) {
+    if (warp == kEpiWarps) {
         // ===================================== producer =====================================
         // the whole warp walks the loop (warp-uniform control flow); one elected lane issues the copies (tc::elect_one)
         {
@@ -539,7 +540,7 @@ __global__ void __launch_bounds__(kThreadsTc, 1) tc_match_pairs_kernel(const Pai
                 }
             }
         }
-    } else if (warp == 1) {
+    } else if (warp == kEpiWarps + 1) {
         // ===================================== MMA issuer =====================================
         // whole warp in the loop, one elected lane issues: no ELECT / BRA.U.ANY waterfall around every tcgen05.mma
         {
@@ -586,7 +587,7 @@ __global__ void __launch_bounds__(kThreadsTc, 1) tc_match_pairs_kernel(const Pai
         }
     } else {
         // ===================================== epilogue =====================================
-        const int e = warp - 2, q = warp & 3, cp = e >> 2;
+        const int e = warp, q = warp & 3, cp = e >> 2;
         const int et = e * 32 + lane;                         // 0..255 within the epilogue group
         uint8_t* my_scratch = p.scratch + (size_t)blockIdx.x * tc_scratch_bytes_per_cta(p.rows_cap, p.cols_cap);
         long long* colstate = reinterpret_cast<long long*>(my_scratch);                       // [cols_cap][2]
@@ -704,6 +705,7 @@ __global__ void __launch_bounds__(kThreadsTc, 1) tc_match_pairs_kernel(const Pai
                 }
                 epi_bar();
                 if (!kOrb)
+#pragma unroll 4                                                            // independent rows: overlap their gathered loads
                 for (int r = 0; r < kABlockRows / kEpiWarps; ++r) {
                     const uint32_t lr = e * (kABlockRows / kEpiWarps) + r, row = blk0 * 128 + lr;
                     if (row < N && lr < nh * 128) {
@@ -723,6 +725,7 @@ __global__ void __launch_bounds__(kThreadsTc, 1) tc_match_pairs_kernel(const Pai
             if (kOrb) {
                 for (uint32_t j = et; j < M; j += kEpiThreads) m21[j] = comp_ratio(colstate[2 * j], colstate[2 * j + 1], N, p.ratio);
             } else {
+#pragma unroll 4
                 for (uint32_t j = e; j < M; j += kEpiWarps) {
                     const long long k0 = colstate[2 * j], k1 = colstate[2 * j + 1];
                     const uint32_t mm = rerank_ratio_checked(Bf + (size_t)j * 128, Af, (uint32_t)k0, (uint32_t)k1, N, p.ratio, lane, both_exact, __uint_as_float(A.max_norm_bits),
@@ -739,7 +742,7 @@ __global__ void __launch_bounds__(kThreadsTc, 1) tc_match_pairs_kernel(const Pai
     }
     tc::tc_fence_before();
     __syncthreads();
-    if (warp == 1) tc::tmem_dealloc(tmem, 512);
+    if (warp == kEpiWarps + 1) tc::tmem_dealloc(tmem, 512);
 }
 
 }  // namespace tcm
