@@ -14,7 +14,7 @@ KIND_ORB256, KIND_F32X128 = 0, 1
 NONE = 0xFFFFFFFF
 PAIR_GATED, PAIR_CONNECTED = 1, 2
 CFG_SIFT_EXACT_FP32, CFG_ORB_POPC, CFG_ORB_TC_V1, CFG_ORB_TC_ALU_SORT, CFG_MULTI_PARALLEL_H2D = 1, 2, 4, 8, 16
-CFG_MATCH_NO_CACHE, CFG_MATCH_LEGACY = 32, 64
+CFG_MATCH_NO_CACHE, CFG_MATCH_LEGACY, CFG_SIFT_TC_V1 = 32, 64, 128
 ABI_VERSION = 2
 
 

@@ -15,7 +15,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(_HERE, "csrc")
 LIB_PATH = os.path.join(_HERE, "libeacham_gpu.so")
 SOURCES = ["eacham_gpu.cu"]
-HEADERS = ["orb_kernels.cuh", "l2_kernels.cuh", "tc_match_kernels.cuh", "tc_orb_kernels.cuh", "tc_common.cuh", "multi.cuh", "match_single.cuh", "verify_kernels.cuh", os.path.join("..", "..", "include", "eacham_gpu.h")]
+HEADERS = ["orb_kernels.cuh", "l2_kernels.cuh", "tc_match_kernels.cuh", "tc_orb_kernels.cuh", "tc_sift_kernels.cuh", "tc_common.cuh", "multi.cuh", "match_single.cuh", "verify_kernels.cuh", os.path.join("..", "..", "include", "eacham_gpu.h")]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
     "-shared", "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden", "-cudart", "static", "-ldl",

@@ -22,6 +22,7 @@
 #include "orb_kernels.cuh"
 #include "tc_match_kernels.cuh"
 #include "tc_orb_kernels.cuh"
+#include "tc_sift_kernels.cuh"
 #include "verify_kernels.cuh"
 
 namespace {
@@ -694,9 +695,14 @@ int launch_pairs(eacham_gpu_handle* h, const eacham_pair_t* pairs, size_t n_pair
             } else if (kind == EACHAM_KIND_ORB256) {
                 CUDA_TRY(cudaFuncSetAttribute(tcm::tc_match_pairs_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
                 tcm::tc_match_pairs_kernel<true><<<grid, tcm::kThreadsTc, smem, h->stream>>>(p);
-            } else {
+            } else if (h->cfg_flags & EACHAM_CFG_SIFT_TC_V1) {
                 CUDA_TRY(cudaFuncSetAttribute(tcm::tc_match_pairs_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
                 tcm::tc_match_pairs_kernel<false><<<grid, tcm::kThreadsTc, smem, h->stream>>>(p);
+            } else {
+                // default: both directions as pruned thread-local scans over D and D^T (tc_sift_kernels.cuh)
+                const size_t smem3 = sizeof(tcs::SmemSift) + 128;
+                CUDA_TRY(cudaFuncSetAttribute(tcs::sift_tc_match_pairs_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem3));
+                tcs::sift_tc_match_pairs_kernel<<<grid, tcs::kThreads, smem3, h->stream>>>(p);
             }
             CUDA_TRY(cudaGetLastError());
             h->timing.kernel_launches += 1;

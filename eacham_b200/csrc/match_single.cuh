@@ -192,10 +192,14 @@ int match_single_tc(eacham_gpu_handle* h, int kind, const void* query, uint32_t 
                 e = cudaFuncSetAttribute(tco::orb_tc_match_pairs_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
                 if (e == cudaSuccess) tco::orb_tc_match_pairs_kernel<true><<<grid, tco::kThreads, smem, slot.stream>>>(p);
             }
-        } else {
+        } else if (h->cfg_flags & EACHAM_CFG_SIFT_TC_V1) {
             const size_t smem = sizeof(tcm::SmemTc) + 128;
             e = cudaFuncSetAttribute(tcm::tc_match_pairs_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
             if (e == cudaSuccess) tcm::tc_match_pairs_kernel<false><<<grid, tcm::kThreadsTc, smem, slot.stream>>>(p);
+        } else {
+            const size_t smem = sizeof(tcs::SmemSift) + 128;
+            e = cudaFuncSetAttribute(tcs::sift_tc_match_pairs_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            if (e == cudaSuccess) tcs::sift_tc_match_pairs_kernel<<<grid, tcs::kThreads, smem, slot.stream>>>(p);
         }
         if (e == cudaSuccess) e = cudaGetLastError();
     }

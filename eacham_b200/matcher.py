@@ -63,7 +63,7 @@ class FeatureMatcherGpu:
 
     def __init__(self, inliersRatio: float = 0.8, *, ratio: float = 0.8, device: int = 0, min_dir: int = 30,
                  min_mutual: int = 30, cross_check: bool = True, match_buffer_entries: int = 0,
-                 orb_engine: str = "tensor", sift_exact_fp32: bool = False, match_cache: bool = True, match_legacy: bool = False):
+                 orb_engine: str = "tensor", sift_exact_fp32: bool = False, sift_engine: str = "tensor", match_cache: bool = True, match_legacy: bool = False):
         self.inliersRatio = float(inliersRatio)
         self.ratio = float(ratio)
         self.min_dir, self.min_mutual, self.cross_check = int(min_dir), int(min_mutual), bool(cross_check)
@@ -72,7 +72,12 @@ class FeatureMatcherGpu:
         if orb_engine not in engines:
             raise ValueError("orb_engine must be 'tensor' (FP8 tensor-core engine with F16 accumulators and packed epilogue, default), "
                              "'popc' (XOR+POPC kernel), 'tensor_v1' (round-1 tensor kernel) or 'tensor_alu' (default engine, sort-2 on the ALU pipe)")
-        flags = (L.CFG_SIFT_EXACT_FP32 if sift_exact_fp32 else 0) | engines[orb_engine] | (0 if match_cache else L.CFG_MATCH_NO_CACHE) | \
+        sift_engines = {"tensor": 0, "tensor_v1": L.CFG_SIFT_TC_V1, "fp32": L.CFG_SIFT_EXACT_FP32}
+        if sift_engine not in sift_engines:
+            raise ValueError("sift_engine must be 'tensor' (bf16 tensor-core scoring of both directions with pruned scans + exact re-rank, default), "
+                             "'tensor_v1' (round-1 tensor kernel) or 'fp32' (all-FP32 kernels)")
+        self.sift_engine = "fp32" if sift_exact_fp32 else sift_engine
+        flags = (L.CFG_SIFT_EXACT_FP32 if sift_exact_fp32 else 0) | sift_engines[sift_engine] | engines[orb_engine] | (0 if match_cache else L.CFG_MATCH_NO_CACHE) | \
                 (L.CFG_MATCH_LEGACY if match_legacy else 0)
         self.orb_engine = orb_engine
         cfg = L.Config(device=device, max_images=0, match_buffer_entries=match_buffer_entries, flags=flags)

@@ -65,6 +65,7 @@ typedef struct eacham_gpu_handle eacham_gpu_handle;
 #define EACHAM_CFG_ORB_POPC 2u         /* ORB pairs on the XOR+POPC kernel instead of the default tensor-core engine (bits as FP8 0/1, exact) */
 #define EACHAM_CFG_ORB_TC_V1 4u        /* ORB pairs on the round-1 tensor-core kernel (F32 accumulators, 32-bit keys); for A/B measurements   */
 #define EACHAM_CFG_ORB_TC_ALU_SORT 8u  /* default ORB engine with its sort-2 steps on the ALU pipe instead of the FMA pipe; for A/B measurements */
+#define EACHAM_CFG_SIFT_TC_V1 128u     /* SIFT pairs on the round-1 tensor-core kernel (one MMA pass, REDUX column path); for A/B measurements */
 #define EACHAM_CFG_MATCH_NO_CACHE 32u  /* eacham_gpu_match: do not keep descriptors on the device between calls (see eacham_gpu_match) */
 #define EACHAM_CFG_MATCH_LEGACY 64u    /* eacham_gpu_match on the round-1 CUDA-core kernels (upload both images per call, one call at a time) */
 #define EACHAM_CFG_MULTI_PARALLEL_H2D 16u /* eacham_gpu_create_multi: one H2D copy per device instead of H2D + NCCL broadcast (no NCCL needed) */

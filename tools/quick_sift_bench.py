@@ -6,7 +6,8 @@ from eacham_b200 import synth
 n_img = int(sys.argv[1]) if len(sys.argv) > 1 else 40
 imgs = synth.sift_image_set_pooled(n_img, 8192, seed=3)
 pairs = synth.exhaustive_pairs(n_img)
-with eacham_b200.FeatureMatcherGpu(0.8) as m:
+engine = sys.argv[2] if len(sys.argv) > 2 else "tensor"
+with eacham_b200.FeatureMatcherGpu(0.8, sift_engine=engine) as m:
     m.Upload(imgs)
     m.MatchPairsDevice(pairs)
     ms = []
@@ -14,4 +15,4 @@ with eacham_b200.FeatureMatcherGpu(0.8) as m:
         m.flush_l2(256 << 20)
         m.MatchPairsDevice(pairs)
         ms.append(m.timing()["kernel_ms"])
-    print({"pairs": len(pairs), "kernel_ms": [round(x, 2) for x in ms], "pairs_per_s": round(len(pairs) / (min(ms) * 1e-3)), "exact_fallbacks": m.timing()["exact_fallbacks"]})
+    print({"engine": engine, "pairs": len(pairs), "kernel_ms": [round(x, 2) for x in ms], "pairs_per_s": round(len(pairs) / (min(ms) * 1e-3)), "exact_fallbacks": m.timing()["exact_fallbacks"]})
