@@ -65,24 +65,34 @@ constexpr int kAugChunkN = tc::kDataChunks + tc::kAugChunks;        // augmentat
 struct SmemSift {
     uint8_t a[kAChunks * kAChunkStride];          // 256 rows of `first`: chunk c, half h, row r at c * 4096 + h * 2048 + r * 16 (rows contiguous: N = 256 operand)
     uint8_t b[kBStages][tc::kBlockBytes];         // 128 rows of `second`, whole pre-tiled block (both augmentations)
-    long long rowstate[kABlockRows][2];           // merged (best, second) composites of the resident rows
-    int32_t rowbar[kABlockRows];                  // their bar: scores >= bar cannot enter the state
-    uint2 slots1[kColParts][kABlockRows];         // tile-local candidates of D1, per column part
-    uint2 slots2[kColParts][128];                 // tile-local candidates of D2, per column part
+    long long rowstate[kABlockRows][2];           // merged (best, second) composites of the resident rows, built at the end of a row block
+    uint2 share1[kColParts][kABlockRows];         // D1: every column part's running (best, second) keys of the resident rows -- the other parts' bars
+    uint32_t tiles1[kColParts][kABlockRows];      // D1: their tile ids (t0 | t1 << 16), published at the end of a row block
     uint64_t b_full[kBStages], b_empty[kBStages], a_full, a_empty, acc_full[2], acc_empty[2];
     uint32_t tmem_slot;
     uint32_t red[2 * kEpiWarps + 8];
     unsigned long long base;
 };
 
-__device__ __forceinline__ void quad_bar(int q) { asm volatile("bar.sync %0, 128;" ::"r"(2 + q) : "memory"); }
-
-// the bar that belongs to a state whose second-best composite has the value word `hi` (= key >> 8): a score can still enter
-// (or tie, and win on the index) iff (score bits & ~0xFF) <= hi << 8, i.e. iff score bits < (hi + 1) << 8
-__device__ __forceinline__ int32_t bar_of(int32_t hi) { return min((hi + 1) << 8, kEmptyKeyTc); }
+// The bar of a query from the running (best, second) keys of its four column parts: the second smallest of the eight keys, rounded
+// up to the next multiple of 256. A score can still enter the merged top two (or tie with its second and win on the index) only
+// if (score bits & ~0xFF) <= second & ~0xFF, i.e. iff score bits < bar. Any STALE copy of a part's keys gives a valid (higher) bar.
+__device__ __forceinline__ int32_t bar_of8(uint2 a, uint2 b, uint2 c, uint2 d) {
+    const int32_t a0 = (int32_t)a.x, b0 = (int32_t)b.x, c0 = (int32_t)c.x, d0 = (int32_t)d.x;
+    const int32_t lo01 = min(a0, b0), hi01 = max(a0, b0), lo23 = min(c0, d0), hi23 = max(c0, d0);
+    const int32_t x = min(min(hi01, hi23), max(lo01, lo23));                                     // second smallest of the four bests
+    const int32_t y = min(min((int32_t)a.y, (int32_t)b.y), min((int32_t)c.y, (int32_t)d.y));     // smallest of the four seconds
+    return (min(x, y) + 255) & ~255;
+}
 
 __device__ __forceinline__ long long comp_of(uint32_t key, uint32_t base) {
     return ((long long)((int32_t)key >> 8) << 32) | (long long)(base + (key & 0xFFu));
+}
+
+// coarse index (tile / row block id) of the two running candidates after a tile: (o0, o1) the keys before it
+__device__ __forceinline__ void track(int32_t m0, int32_t m1, int32_t o0, int32_t o1, uint32_t t, uint32_t& t0, uint32_t& t1) {
+    if (m0 != o0) { t1 = (m1 == o0) ? t0 : t; t0 = t; }
+    else if (m1 != o1) t1 = t;
 }
 
 // key = (score bits & mask) | index byte as ONE LOP3: mask in a register, index immediate
@@ -226,6 +236,117 @@ __device__ __noinline__ void rerank_range(const long long* state, uint32_t s_fir
     }
 }
 
+// The sweep of one resident row block over all tiles of the second image, for one epilogue warp. Leaves the part's keys in S.share1 and
+// its tile ids in S.tiles1; returns the advanced MMA step counter. Not inlined: the loop gets its own register allocation (inlined into
+// the kernel it ran at the 96-register cap with spills inside the tile loop).
+__device__ __noinline__ uint32_t scan_block(SmemSift& S, uint32_t tmem, int q, int cp, int lane, int e, uint32_t blk0, uint32_t nh, uint32_t nbt, uint32_t N, uint32_t M,
+                                            uint32_t ab, bool both, uint2* colkeys, uint32_t* coltiles, uint32_t step_it) {
+    uint32_t mask = 0xFFFFFF00u;
+    asm volatile("" : "+r"(mask));                       // keep the mask in a register: key = (v & mask) | immediate is one LOP3
+    // this part's running candidates of its two resident rows (keys: score bits | column within the part), and their tiles
+    int32_t m0[2] = {kEmptyKeyTc, kEmptyKeyTc}, m1[2] = {kEmptyKeyTc, kEmptyKeyTc};
+    uint32_t t0[2] = {0xFFFFu, 0xFFFFu}, t1[2] = {0xFFFFu, 0xFFFFu};
+    const int r0 = q * 32 + lane, r1 = 128 + q * 32 + lane;
+    const bool rv0 = blk0 * 128 + r0 < N, rv1 = nh == 2 && blk0 * 128 + r1 < N;
+    S.share1[cp][r0] = make_uint2((uint32_t)kEmptyKeyTc, (uint32_t)kEmptyKeyTc);
+    S.share1[cp][r1] = make_uint2((uint32_t)kEmptyKeyTc, (uint32_t)kEmptyKeyTc);
+    epi_bar();                                   // nobody reads the previous block's keys as bars (also orders the column state init)
+    for (uint32_t bt = 0; bt < nbt; ++bt) {
+        const uint32_t jrow = bt * 128 + q * 32 + lane;
+    if (both) {                                      // this tile's rows of the second image: pull their state into L1 ahead of D2
+        asm volatile("prefetch.global.L1 [%0];" ::"l"(colkeys + 4 * (size_t)jrow));
+        asm volatile("prefetch.global.L1 [%0];" ::"l"(coltiles + 4 * (size_t)jrow));
+    }
+        // ---------------- D1: each lane owns one row of each resident half; 32 columns per warp ----------------
+        {
+            const uint32_t reg = step_it & 1;
+            // bars from all four parts' published keys (unsynchronised: stale is fine); padding rows never take part
+            int32_t bar[2] = {INT32_MIN, INT32_MIN};
+            if (rv0) bar[0] = bar_of8(S.share1[0][r0], S.share1[1][r0], S.share1[2][r0], S.share1[3][r0]);
+            if (rv1) bar[1] = bar_of8(S.share1[0][r1], S.share1[1][r1], S.share1[2][r1], S.share1[3][r1]);
+            const int32_t o00 = m0[0], o10 = m1[0], o01 = m0[1], o11 = m1[1];
+            if (lane == 0 && (e == 0 || e == 5)) SIFT_TRACE(e == 5, step_it >> 1, 0);
+            tc::mbar_wait(&S.acc_full[reg], (step_it >> 1) & 1);
+            tc::tc_fence_after();
+            if (lane == 0 && (e == 0 || e == 5)) SIFT_TRACE(e == 5, step_it >> 1, 1);
+            const uint32_t taddr = tmem + reg * 256 + ((uint32_t)(q * 32) << 16) + cp * 32;
+            {
+                // 16-column loads, ping-pong: the next load is in flight while this one is scanned
+                uint32_t v[16], w[16];
+                tc::tmem_ld16(taddr, v);
+                tc::tmem_ld_wait();
+                tc::tmem_ld16(taddr + 16, w);
+                scan16<0>(v, mask, m0[0], m1[0], bar[0]);
+                tc::tmem_ld_wait();
+                if (nh == 2) tc::tmem_ld16(taddr + 128, v);
+                scan16<16>(w, mask, m0[0], m1[0], bar[0]);
+                if (nh == 2) {
+                    tc::tmem_ld_wait();
+                    tc::tmem_ld16(taddr + 144, w);
+                    scan16<0>(v, mask, m0[1], m1[1], bar[1]);
+                    tc::tmem_ld_wait();
+                    scan16<16>(w, mask, m0[1], m1[1], bar[1]);
+                }
+            }
+            tc::tc_fence_before();
+            __syncwarp();
+            if (lane == 0) tc::mbar_arrive(&S.acc_empty[reg]);
+            if (lane == 0 && (e == 0 || e == 5)) SIFT_TRACE(e == 5, step_it >> 1, 2);
+            ++step_it;
+            track(m0[0], m1[0], o00, o10, bt, t0[0], t1[0]);
+            track(m0[1], m1[1], o01, o11, bt, t0[1], t1[1]);
+            S.share1[cp][r0] = make_uint2((uint32_t)m0[0], (uint32_t)m1[0]);
+            if (nh == 2) S.share1[cp][r1] = make_uint2((uint32_t)m0[1], (uint32_t)m1[1]);
+        }
+        if (lane == 0 && (e == 0 || e == 5)) SIFT_TRACE(e == 5, (step_it - 1) >> 1, 3);
+        if (!both) continue;
+        // ---------------- D2: each lane owns one row of the streamed tile; 64 columns (resident rows) per warp ----------------
+        {
+            const uint32_t reg = step_it & 1;
+            const uint32_t ncols = nh * 128;
+            const uint4 ka = reinterpret_cast<const uint4*>(colkeys)[2 * (size_t)jrow], kb = reinterpret_cast<const uint4*>(colkeys)[2 * (size_t)jrow + 1];
+            const uint2 own = colkeys[4 * (size_t)jrow + cp];
+            uint32_t tt = coltiles[4 * (size_t)jrow + cp];
+            int32_t c0 = (int32_t)own.x, c1 = (int32_t)own.y;
+            int32_t bar = jrow < M ? bar_of8(make_uint2(ka.x, ka.y), make_uint2(ka.z, ka.w), make_uint2(kb.x, kb.y), make_uint2(kb.z, kb.w)) : INT32_MIN;
+            tc::mbar_wait(&S.acc_full[reg], (step_it >> 1) & 1);
+            tc::tc_fence_after();
+            if (lane == 0 && (e == 0 || e == 5)) SIFT_TRACE(e == 5, step_it >> 1, 4);
+            const uint32_t taddr = tmem + reg * 256 + ((uint32_t)(q * 32) << 16) + cp * 64;
+            if ((uint32_t)cp * 64 < ncols) {
+                uint32_t v[16], w[16];                      // cp * 64 + 64 <= ncols too: ncols is 128 or 256
+                tc::tmem_ld16(taddr, v);
+                tc::tmem_ld_wait();
+                tc::tmem_ld16(taddr + 16, w);
+                scan16<0>(v, mask, c0, c1, bar);
+                tc::tmem_ld_wait();
+                tc::tmem_ld16(taddr + 32, v);
+                scan16<16>(w, mask, c0, c1, bar);
+                tc::tmem_ld_wait();
+                tc::tmem_ld16(taddr + 48, w);
+                scan16<32>(v, mask, c0, c1, bar);
+                tc::tmem_ld_wait();
+                scan16<48>(w, mask, c0, c1, bar);
+            }
+            tc::tc_fence_before();
+            __syncwarp();
+            if (lane == 0) tc::mbar_arrive(&S.acc_empty[reg]);
+            if (lane == 0 && (e == 0 || e == 5)) SIFT_TRACE(e == 5, step_it >> 1, 5);
+            ++step_it;
+            if (c0 != (int32_t)own.x || c1 != (int32_t)own.y) {
+                uint32_t u0 = tt & 0xFFFFu, u1 = tt >> 16;
+                track(c0, c1, (int32_t)own.x, (int32_t)own.y, ab, u0, u1);
+                colkeys[4 * (size_t)jrow + cp] = make_uint2((uint32_t)c0, (uint32_t)c1);
+                coltiles[4 * (size_t)jrow + cp] = u0 | (u1 << 16);
+            }
+            if (lane == 0 && (e == 0 || e == 5)) SIFT_TRACE(e == 5, (step_it - 1) >> 1, 6);
+        }
+    }
+    S.tiles1[cp][r0] = t0[0] | (t1[0] << 16);
+    S.tiles1[cp][r1] = t0[1] | (t1[1] << 16);
+    return step_it;
+}
+
 // =============================================================================================================
 // The fused SIFT pair kernel: one persistent CTA per SM, pairs in the host's L2-blocked order. 576 threads:
 //   warps 0-15 epilogue (4 per TMEM lane quadrant; column part cp = warp / 4)
@@ -360,13 +481,12 @@ __global__ void __launch_bounds__(kThreads, 1) sift_tc_match_pairs_kernel(const 
         const int e = warp, q = warp & 3, cp = e >> 2;
         const int et = e * 32 + lane;
         uint8_t* my_scratch = p.scratch + (size_t)blockIdx.x * tcm::tc_scratch_bytes_per_cta(p.rows_cap, p.cols_cap);
-        long long* colstate = reinterpret_cast<long long*>(my_scratch);                        // [cols_cap][2]
-        uint32_t* m12 = reinterpret_cast<uint32_t*>(my_scratch + (size_t)p.cols_cap * 16);     // [rows_cap]
-        uint32_t* m21 = m12 + p.rows_cap;                                                      // [cols_cap]
-        uint32_t mask = 0xFFFFFF00u;
-        asm volatile("" : "+r"(mask));                       // keep the mask in a register: key = (v & mask) | immediate is one LOP3
+        uint2* colkeys = reinterpret_cast<uint2*>(my_scratch);                                      // [cols_cap][4 parts]: running (best, second) keys
+        uint32_t* coltiles = reinterpret_cast<uint32_t*>(my_scratch + (size_t)p.cols_cap * 32);     // [cols_cap][4 parts]: their row-block ids
+        long long* colstate = reinterpret_cast<long long*>(my_scratch + (size_t)p.cols_cap * 48);   // [cols_cap][2]: merged composites (end of pair)
+        uint32_t* m12 = reinterpret_cast<uint32_t*>(my_scratch + (size_t)p.cols_cap * 64);          // [rows_cap]
+        uint32_t* m21 = m12 + p.rows_cap;                                                           // [cols_cap]
         uint32_t step_it = 0;
-        for (int i = et; i < kABlockRows; i += kEpiThreads) { S.rowstate[i][0] = kEmptyComp; S.rowstate[i][1] = kEmptyComp; S.rowbar[i] = kEmptyKeyTc; }
         for (uint32_t wk = blockIdx.x; wk < p.n_pairs; wk += gridDim.x) {
             const uint32_t pi = p.single_dir ? wk : p.order[wk];
             const eacham_pair_t pr = p.pairs[p.single_dir ? 0u : pi];
@@ -385,141 +505,51 @@ __global__ void __launch_bounds__(kThreads, 1) sift_tc_match_pairs_kernel(const 
             const bool both_exact = A.bf16_exact != 0 && B.bf16_exact != 0;
             const uint32_t na128 = (N + 127) / 128, nbt = (M + 127) / 128;
             if (both)
-                for (uint32_t j = et; j < nbt * 128; j += kEpiThreads) { colstate[2 * j] = kEmptyComp; colstate[2 * j + 1] = kEmptyComp; }
-            epi_bar();
+                for (uint32_t j = et; j < nbt * 128; j += kEpiThreads) {
+                    const uint4 ek = make_uint4((uint32_t)kEmptyKeyTc, (uint32_t)kEmptyKeyTc, (uint32_t)kEmptyKeyTc, (uint32_t)kEmptyKeyTc);
+                    reinterpret_cast<uint4*>(colkeys)[2 * (size_t)j] = ek;
+                    reinterpret_cast<uint4*>(colkeys)[2 * (size_t)j + 1] = ek;
+                    reinterpret_cast<uint4*>(coltiles)[j] = make_uint4(0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu);
+                }
 
             for (uint32_t ab = p.single_dir ? pi : 0u, ab1 = p.single_dir ? pi + 1 : (na128 + 1) / 2; ab < ab1; ++ab) {
                 const uint32_t blk0 = p.single_dir ? pi : ab * 2;
                 const uint32_t nh = p.single_dir ? 1u : min(2u, na128 - ab * 2);
-                for (uint32_t bt = 0; bt < nbt; ++bt) {
-                    // second image's state of this tile's rows: issue the (L2) load early
-                    longlong2 cs = make_longlong2(0, 0);
-                    const uint32_t jrow = bt * 128 + q * 32 + lane;
-                    if (both) cs = *reinterpret_cast<const longlong2*>(colstate + 2 * (size_t)jrow);
-                    // ---------------- D1: each lane owns one row of each resident half; 32 columns per warp ----------------
-                    {
-                        const uint32_t reg = step_it & 1;
-                        int32_t c0[2] = {kEmptyKeyTc, kEmptyKeyTc}, c1[2] = {kEmptyKeyTc, kEmptyKeyTc}, bar[2];
-                        // padding rows (beyond N) never take part: a bar below every score
-                        bar[0] = (blk0 * 128 + q * 32 + lane < N) ? S.rowbar[q * 32 + lane] : INT32_MIN;
-                        bar[1] = (blk0 * 128 + 128 + q * 32 + lane < N) ? S.rowbar[128 + q * 32 + lane] : INT32_MIN;
-                        // single-direction mode has one barrier per tile, so its hand-over slots alternate between the two halves of slots1
-                        const int sb = both ? 0 : (int)(bt & 1u) * 128;
-                        if (lane == 0 && (e == 0 || e == 5)) SIFT_TRACE(e == 5, step_it >> 1, 0);
-                        tc::mbar_wait(&S.acc_full[reg], (step_it >> 1) & 1);
-                        tc::tc_fence_after();
-                        if (lane == 0 && (e == 0 || e == 5)) SIFT_TRACE(e == 5, step_it >> 1, 1);
-                        const uint32_t taddr = tmem + reg * 256 + ((uint32_t)(q * 32) << 16) + cp * 32;
-                        {
-                            // 16-column loads, ping-pong: the next load is in flight while this one is scanned
-                            uint32_t v[16], w[16];
-                            tc::tmem_ld16(taddr, v);
-                            tc::tmem_ld_wait();
-                            tc::tmem_ld16(taddr + 16, w);
-                            scan16<0>(v, mask, c0[0], c1[0], bar[0]);
-                            tc::tmem_ld_wait();
-                            if (nh == 2) tc::tmem_ld16(taddr + 128, v);
-                            scan16<16>(w, mask, c0[0], c1[0], bar[0]);
-                            if (nh == 2) {
-                                tc::tmem_ld_wait();
-                                tc::tmem_ld16(taddr + 144, w);
-                                scan16<0>(v, mask, c0[1], c1[1], bar[1]);
-                                tc::tmem_ld_wait();
-                                scan16<16>(w, mask, c0[1], c1[1], bar[1]);
-                            }
-                        }
-                        tc::tc_fence_before();
-                        __syncwarp();
-                        if (lane == 0) tc::mbar_arrive(&S.acc_empty[reg]);
-                        if (lane == 0 && (e == 0 || e == 5)) SIFT_TRACE(e == 5, step_it >> 1, 2);
-                        ++step_it;
-                        S.slots1[cp][sb + q * 32 + lane] = make_uint2((uint32_t)c0[0], (uint32_t)c1[0]);
-                        if (nh == 2) S.slots1[cp][128 + q * 32 + lane] = make_uint2((uint32_t)c0[1], (uint32_t)c1[1]);
-                        quad_bar(q);
-                        if (cp == (int)(bt & 3u)) {
+                step_it = scan_block(S, tmem, q, cp, lane, e, blk0, nh, nbt, N, M, ab, both, colkeys, coltiles, step_it);
+                // ---- rows of this block are complete: merge the four parts, re-rank exactly, ratio test ----
+                epi_bar();
+                if (et < kABlockRows) {
+                    long long g0 = kEmptyComp, g1 = kEmptyComp;
 #pragma unroll
-                            for (int h = 0; h < 2; ++h) {
-                                if (h < (int)nh) {
-                                    const int row = h * 128 + q * 32 + lane;
-                                    const int32_t bar0 = S.rowbar[row];
-                                    const uint2 s0 = S.slots1[0][sb + row], s1 = S.slots1[1][sb + row], s2 = S.slots1[2][sb + row], s3 = S.slots1[3][sb + row];
-                                    if (min(min((int32_t)s0.x, (int32_t)s1.x), min((int32_t)s2.x, (int32_t)s3.x)) < bar0) {
-                                        long long g0 = S.rowstate[row][0], g1 = S.rowstate[row][1];
-                                        const uint32_t base = bt * 128;
-                                        if ((int32_t)s0.x < bar0) tcm::comp_merge(comp_of(s0.x, base), comp_of(s0.y, base), g0, g1);
-                                        if ((int32_t)s1.x < bar0) tcm::comp_merge(comp_of(s1.x, base + 32), comp_of(s1.y, base + 32), g0, g1);
-                                        if ((int32_t)s2.x < bar0) tcm::comp_merge(comp_of(s2.x, base + 64), comp_of(s2.y, base + 64), g0, g1);
-                                        if ((int32_t)s3.x < bar0) tcm::comp_merge(comp_of(s3.x, base + 96), comp_of(s3.y, base + 96), g0, g1);
-                                        S.rowstate[row][0] = g0; S.rowstate[row][1] = g1;
-                                        S.rowbar[row] = bar_of((int32_t)(g1 >> 32));
-                                    }
-                                }
-                            }
-                        }
+                    for (int c = 0; c < kColParts; ++c) {
+                        const uint2 k = S.share1[c][et];
+                        const uint32_t tl = S.tiles1[c][et];
+                        tcm::comp_merge(comp_of(k.x, (tl & 0xFFFFu) * 128 + c * 32), comp_of(k.y, (tl >> 16) * 128 + c * 32), g0, g1);
                     }
-                    if (lane == 0 && (e == 0 || e == 5)) SIFT_TRACE(e == 5, (step_it - 1) >> 1, 3);
-                    if (!both) continue;
-                    // ---------------- D2: each lane owns one row of the streamed tile; 64 columns (resident rows) per warp ----------------
-                    {
-                        const uint32_t reg = step_it & 1;
-                        const uint32_t ncols = nh * 128;
-                        const int32_t bar0 = bar_of((int32_t)(cs.y >> 32));
-                        int32_t c0 = kEmptyKeyTc, c1 = kEmptyKeyTc, bar = jrow < M ? bar0 : INT32_MIN;
-                        tc::mbar_wait(&S.acc_full[reg], (step_it >> 1) & 1);
-                        tc::tc_fence_after();
-                        if (lane == 0 && (e == 0 || e == 5)) SIFT_TRACE(e == 5, step_it >> 1, 4);
-                        const uint32_t taddr = tmem + reg * 256 + ((uint32_t)(q * 32) << 16) + cp * 64;
-                        if ((uint32_t)cp * 64 < ncols) {
-                            uint32_t v[16], w[16];                      // cp * 64 + 64 <= ncols too: ncols is 128 or 256
-                            tc::tmem_ld16(taddr, v);
-                            tc::tmem_ld_wait();
-                            tc::tmem_ld16(taddr + 16, w);
-                            scan16<0>(v, mask, c0, c1, bar);
-                            tc::tmem_ld_wait();
-                            tc::tmem_ld16(taddr + 32, v);
-                            scan16<16>(w, mask, c0, c1, bar);
-                            tc::tmem_ld_wait();
-                            tc::tmem_ld16(taddr + 48, w);
-                            scan16<32>(v, mask, c0, c1, bar);
-                            tc::tmem_ld_wait();
-                            scan16<48>(w, mask, c0, c1, bar);
-                        }
-                        tc::tc_fence_before();
-                        __syncwarp();
-                        if (lane == 0) tc::mbar_arrive(&S.acc_empty[reg]);
-                        if (lane == 0 && (e == 0 || e == 5)) SIFT_TRACE(e == 5, step_it >> 1, 5);
-                        ++step_it;
-                        S.slots2[cp][q * 32 + lane] = make_uint2((uint32_t)c0, (uint32_t)c1);
-                        quad_bar(q);
-                        if (cp == (int)((bt + 2) & 3u)) {
-                            const int r = q * 32 + lane;
-                            const uint2 s0 = S.slots2[0][r], s1 = S.slots2[1][r], s2 = S.slots2[2][r], s3 = S.slots2[3][r];
-                            if (min(min((int32_t)s0.x, (int32_t)s1.x), min((int32_t)s2.x, (int32_t)s3.x)) < bar0) {
-                                long long g0 = cs.x, g1 = cs.y;
-                                const uint32_t base = blk0 * 128;
-                                if ((int32_t)s0.x < bar0) tcm::comp_merge(comp_of(s0.x, base), comp_of(s0.y, base), g0, g1);
-                                if ((int32_t)s1.x < bar0) tcm::comp_merge(comp_of(s1.x, base + 64), comp_of(s1.y, base + 64), g0, g1);
-                                if ((int32_t)s2.x < bar0) tcm::comp_merge(comp_of(s2.x, base + 128), comp_of(s2.y, base + 128), g0, g1);
-                                if ((int32_t)s3.x < bar0) tcm::comp_merge(comp_of(s3.x, base + 192), comp_of(s3.y, base + 192), g0, g1);
-                                *reinterpret_cast<longlong2*>(colstate + 2 * (size_t)jrow) = make_longlong2(g0, g1);
-                            }
-                        }
-                        if (lane == 0 && (e == 0 || e == 5)) SIFT_TRACE(e == 5, (step_it - 1) >> 1, 6);
-                    }
+                    S.rowstate[et][0] = g0; S.rowstate[et][1] = g1;
                 }
-                // ---- rows of this block are complete: re-rank exactly, ratio test ----
-                epi_bar();                                                  // every tile's merge is in rowstate
+                epi_bar();
                 rerank_range(&S.rowstate[0][0], e * (kABlockRows / kEpiWarps), blk0 * 128 + e * (kABlockRows / kEpiWarps), 1, kABlockRows / kEpiWarps,
                              min(N, (blk0 + nh) * 128), Af, Bf, M, p.ratio, lane, both_exact, __uint_as_float(A.max_norm_bits), __uint_as_float(B.max_norm_bits), p.exact_fallbacks,
                              p.dbg_idx12, p.dbg_dist12, p.single_dir ? p.single_out : m12);
-                epi_bar();
-                for (int i = et; i < kABlockRows; i += kEpiThreads) { S.rowstate[i][0] = kEmptyComp; S.rowstate[i][1] = kEmptyComp; S.rowbar[i] = kEmptyKeyTc; }
-                epi_bar();
             }
 
             if (p.single_dir) continue;                       // one direction only
-            // ---- rows of `second`: re-rank, ratio -> m21 ----
+            // ---- rows of `second`: merge the four parts, re-rank, ratio -> m21 ----
             __threadfence_block();
+            epi_bar();
+            for (uint32_t j = et; j < M; j += kEpiThreads) {
+                const uint4 ka = reinterpret_cast<const uint4*>(colkeys)[2 * (size_t)j], kb = reinterpret_cast<const uint4*>(colkeys)[2 * (size_t)j + 1];
+                const uint4 tl = reinterpret_cast<const uint4*>(coltiles)[j];
+                long long g0 = kEmptyComp, g1 = kEmptyComp;
+                tcm::comp_merge(comp_of(ka.x, (tl.x & 0xFFFFu) * 256), comp_of(ka.y, (tl.x >> 16) * 256), g0, g1);
+                tcm::comp_merge(comp_of(ka.z, (tl.y & 0xFFFFu) * 256 + 64), comp_of(ka.w, (tl.y >> 16) * 256 + 64), g0, g1);
+                tcm::comp_merge(comp_of(kb.x, (tl.z & 0xFFFFu) * 256 + 128), comp_of(kb.y, (tl.z >> 16) * 256 + 128), g0, g1);
+                tcm::comp_merge(comp_of(kb.z, (tl.w & 0xFFFFu) * 256 + 192), comp_of(kb.w, (tl.w >> 16) * 256 + 192), g0, g1);
+                colstate[2 * (size_t)j] = g0; colstate[2 * (size_t)j + 1] = g1;
+            }
+            __threadfence_block();
+            epi_bar();
             rerank_range(colstate, e, e, kEpiWarps, (M + kEpiWarps - 1 - e) / kEpiWarps, M, Bf, Af, N, p.ratio, lane, both_exact, __uint_as_float(B.max_norm_bits), __uint_as_float(A.max_norm_bits),
                          p.exact_fallbacks, p.dbg_idx21, p.dbg_dist21, m21);
             __threadfence_block();
