@@ -34,6 +34,15 @@
 #ifndef EACHAM_EXP
 #define EACHAM_EXP 0
 #endif
+#ifndef SIFT_BAR_EVERY
+#define SIFT_BAR_EVERY 4      // D1: the other parts' keys are re-read every this many tiles (power of two)
+#endif
+#ifndef SIFT_SUBGROUPS
+#define SIFT_SUBGROUPS 0      // a hit group of eight is narrowed to the sub-groups (3 + 3 + 2 scores) whose partial minimum is under a bar
+#endif
+#ifndef SIFT_TREE_BODY
+#define SIFT_TREE_BODY 0      // insertion of eight keys as a sort-2 / merge tree (1) or a chain of eight insertions (0)
+#endif
 
 namespace eacham {
 namespace tcs {
@@ -113,12 +122,42 @@ template <int kIdx0, int kOff>
 __device__ __forceinline__ void scan8(const uint32_t (&v)[16], uint32_t mask, int32_t& c0, int32_t& c1, int32_t& bar) {
     const int32_t x0 = (int32_t)v[kOff + 0], x1 = (int32_t)v[kOff + 1], x2 = (int32_t)v[kOff + 2], x3 = (int32_t)v[kOff + 3];
     const int32_t x4 = (int32_t)v[kOff + 4], x5 = (int32_t)v[kOff + 5], x6 = (int32_t)v[kOff + 6], x7 = (int32_t)v[kOff + 7];
-    const int32_t mn = min(min(min(x0, x1), x2), min(min(min(x3, x4), x5), min(x6, x7)));
+    const int32_t ga = min(min(x0, x1), x2), gb = min(min(x3, x4), x5), gc = min(x6, x7);
+    const int32_t mn = min(min(ga, gb), gc);
     if (__any_sync(0xffffffffu, mn < bar)) {
+#if SIFT_SUBGROUPS
+        // second level: the three partial minima of the tree say which of the groups {0,1,2} {3,4,5} {6,7} hold the score(s) under a bar;
+        // typically one lane, one score -- so one group's insertions instead of all eight
+        if (__any_sync(0xffffffffu, ga < bar)) {
+            insert(key_of<kIdx0 + 0>(v[kOff + 0], mask), c0, c1); insert(key_of<kIdx0 + 1>(v[kOff + 1], mask), c0, c1);
+            insert(key_of<kIdx0 + 2>(v[kOff + 2], mask), c0, c1);
+        }
+        if (__any_sync(0xffffffffu, gb < bar)) {
+            insert(key_of<kIdx0 + 3>(v[kOff + 3], mask), c0, c1); insert(key_of<kIdx0 + 4>(v[kOff + 4], mask), c0, c1);
+            insert(key_of<kIdx0 + 5>(v[kOff + 5], mask), c0, c1);
+        }
+        if (__any_sync(0xffffffffu, gc < bar)) {
+            insert(key_of<kIdx0 + 6>(v[kOff + 6], mask), c0, c1); insert(key_of<kIdx0 + 7>(v[kOff + 7], mask), c0, c1);
+        }
+#elif SIFT_TREE_BODY
+        // top two of the eight keys by a sort-2 / merge tree (depth 7 instead of a 16-deep insertion chain), then into the state
+        const int32_t k0 = key_of<kIdx0 + 0>(v[kOff + 0], mask), k1 = key_of<kIdx0 + 1>(v[kOff + 1], mask);
+        const int32_t k2 = key_of<kIdx0 + 2>(v[kOff + 2], mask), k3 = key_of<kIdx0 + 3>(v[kOff + 3], mask);
+        const int32_t k4 = key_of<kIdx0 + 4>(v[kOff + 4], mask), k5 = key_of<kIdx0 + 5>(v[kOff + 5], mask);
+        const int32_t k6 = key_of<kIdx0 + 6>(v[kOff + 6], mask), k7 = key_of<kIdx0 + 7>(v[kOff + 7], mask);
+        const int32_t a0 = min(k0, k1), a1 = max(k0, k1), b0 = min(k2, k3), b1 = max(k2, k3);
+        const int32_t d0 = min(k4, k5), d1 = max(k4, k5), e0 = min(k6, k7), e1 = max(k6, k7);
+        const int32_t f0 = min(a0, b0), f1 = min(min(max(a0, b0), a1), b1);
+        const int32_t g0 = min(d0, e0), g1 = min(min(max(d0, e0), d1), e1);
+        const int32_t h0 = min(f0, g0), h1 = min(min(max(f0, g0), f1), g1);
+        c1 = min(min(max(c0, h0), c1), h1);
+        c0 = min(c0, h0);
+#else
         insert(key_of<kIdx0 + 0>(v[kOff + 0], mask), c0, c1); insert(key_of<kIdx0 + 1>(v[kOff + 1], mask), c0, c1);
         insert(key_of<kIdx0 + 2>(v[kOff + 2], mask), c0, c1); insert(key_of<kIdx0 + 3>(v[kOff + 3], mask), c0, c1);
         insert(key_of<kIdx0 + 4>(v[kOff + 4], mask), c0, c1); insert(key_of<kIdx0 + 5>(v[kOff + 5], mask), c0, c1);
         insert(key_of<kIdx0 + 6>(v[kOff + 6], mask), c0, c1); insert(key_of<kIdx0 + 7>(v[kOff + 7], mask), c0, c1);
+#endif
         bar = min(bar, (c1 + 255) & ~255);
     }
 }
@@ -251,19 +290,26 @@ __device__ __noinline__ uint32_t scan_block(SmemSift& S, uint32_t tmem, int q, i
     S.share1[cp][r0] = make_uint2((uint32_t)kEmptyKeyTc, (uint32_t)kEmptyKeyTc);
     S.share1[cp][r1] = make_uint2((uint32_t)kEmptyKeyTc, (uint32_t)kEmptyKeyTc);
     epi_bar();                                   // nobody reads the previous block's keys as bars (also orders the column state init)
+    int32_t bar1[2] = {rv0 ? kEmptyKeyTc : INT32_MIN, rv1 ? kEmptyKeyTc : INT32_MIN};      // D1 bars, carried from tile to tile
     for (uint32_t bt = 0; bt < nbt; ++bt) {
         const uint32_t jrow = bt * 128 + q * 32 + lane;
-    if (both) {                                      // this tile's rows of the second image: pull their state into L1 ahead of D2
-        asm volatile("prefetch.global.L1 [%0];" ::"l"(colkeys + 4 * (size_t)jrow));
-        asm volatile("prefetch.global.L1 [%0];" ::"l"(coltiles + 4 * (size_t)jrow));
-    }
+        // this tile's rows of the second image: their four parts' keys and this part's block ids, requested ahead of D2 (L2 latency)
+        uint4 ka = make_uint4(0u, 0u, 0u, 0u), kb = ka;
+        uint32_t tt = 0;
+        if (both) {
+            ka = reinterpret_cast<const uint4*>(colkeys)[2 * (size_t)jrow];
+            kb = reinterpret_cast<const uint4*>(colkeys)[2 * (size_t)jrow + 1];
+            tt = coltiles[4 * (size_t)jrow + cp];
+        }
         // ---------------- D1: each lane owns one row of each resident half; 32 columns per warp ----------------
         {
             const uint32_t reg = step_it & 1;
-            // bars from all four parts' published keys (unsynchronised: stale is fine); padding rows never take part
-            int32_t bar[2] = {INT32_MIN, INT32_MIN};
-            if (rv0) bar[0] = bar_of8(S.share1[0][r0], S.share1[1][r0], S.share1[2][r0], S.share1[3][r0]);
-            if (rv1) bar[1] = bar_of8(S.share1[0][r1], S.share1[1][r1], S.share1[2][r1], S.share1[3][r1]);
+            // bars from all four parts' published keys, every fourth tile (unsynchronised: stale only means a higher bar); in between
+            // the bar only follows this part's own insertions. Padding rows never take part.
+            if ((bt & (SIFT_BAR_EVERY - 1u)) == (SIFT_BAR_EVERY > 1 ? 1u : 0u)) {
+                if (rv0) bar1[0] = min(bar1[0], bar_of8(S.share1[0][r0], S.share1[1][r0], S.share1[2][r0], S.share1[3][r0]));
+                if (rv1) bar1[1] = min(bar1[1], bar_of8(S.share1[0][r1], S.share1[1][r1], S.share1[2][r1], S.share1[3][r1]));
+            }
             const int32_t o00 = m0[0], o10 = m1[0], o01 = m0[1], o11 = m1[1];
             if (lane == 0 && (e == 0 || e == 5)) SIFT_TRACE(e == 5, step_it >> 1, 0);
             tc::mbar_wait(&S.acc_full[reg], (step_it >> 1) & 1);
@@ -276,16 +322,16 @@ __device__ __noinline__ uint32_t scan_block(SmemSift& S, uint32_t tmem, int q, i
                 tc::tmem_ld16(taddr, v);
                 tc::tmem_ld_wait();
                 tc::tmem_ld16(taddr + 16, w);
-                scan16<0>(v, mask, m0[0], m1[0], bar[0]);
+                scan16<0>(v, mask, m0[0], m1[0], bar1[0]);
                 tc::tmem_ld_wait();
                 if (nh == 2) tc::tmem_ld16(taddr + 128, v);
-                scan16<16>(w, mask, m0[0], m1[0], bar[0]);
+                scan16<16>(w, mask, m0[0], m1[0], bar1[0]);
                 if (nh == 2) {
                     tc::tmem_ld_wait();
                     tc::tmem_ld16(taddr + 144, w);
-                    scan16<0>(v, mask, m0[1], m1[1], bar[1]);
+                    scan16<0>(v, mask, m0[1], m1[1], bar1[1]);
                     tc::tmem_ld_wait();
-                    scan16<16>(w, mask, m0[1], m1[1], bar[1]);
+                    scan16<16>(w, mask, m0[1], m1[1], bar1[1]);
                 }
             }
             tc::tc_fence_before();
@@ -293,10 +339,12 @@ __device__ __noinline__ uint32_t scan_block(SmemSift& S, uint32_t tmem, int q, i
             if (lane == 0) tc::mbar_arrive(&S.acc_empty[reg]);
             if (lane == 0 && (e == 0 || e == 5)) SIFT_TRACE(e == 5, step_it >> 1, 2);
             ++step_it;
-            track(m0[0], m1[0], o00, o10, bt, t0[0], t1[0]);
-            track(m0[1], m1[1], o01, o11, bt, t0[1], t1[1]);
-            S.share1[cp][r0] = make_uint2((uint32_t)m0[0], (uint32_t)m1[0]);
-            if (nh == 2) S.share1[cp][r1] = make_uint2((uint32_t)m0[1], (uint32_t)m1[1]);
+            if (__any_sync(0xffffffffu, m0[0] != o00 || m1[0] != o10 || m0[1] != o01 || m1[1] != o11)) {     // some row of the warp changed
+                track(m0[0], m1[0], o00, o10, bt, t0[0], t1[0]);
+                track(m0[1], m1[1], o01, o11, bt, t0[1], t1[1]);
+                S.share1[cp][r0] = make_uint2((uint32_t)m0[0], (uint32_t)m1[0]);
+                if (nh == 2) S.share1[cp][r1] = make_uint2((uint32_t)m0[1], (uint32_t)m1[1]);
+            }
         }
         if (lane == 0 && (e == 0 || e == 5)) SIFT_TRACE(e == 5, (step_it - 1) >> 1, 3);
         if (!both) continue;
@@ -304,9 +352,7 @@ __device__ __noinline__ uint32_t scan_block(SmemSift& S, uint32_t tmem, int q, i
         {
             const uint32_t reg = step_it & 1;
             const uint32_t ncols = nh * 128;
-            const uint4 ka = reinterpret_cast<const uint4*>(colkeys)[2 * (size_t)jrow], kb = reinterpret_cast<const uint4*>(colkeys)[2 * (size_t)jrow + 1];
-            const uint2 own = colkeys[4 * (size_t)jrow + cp];
-            uint32_t tt = coltiles[4 * (size_t)jrow + cp];
+            const uint2 own = cp == 0 ? make_uint2(ka.x, ka.y) : cp == 1 ? make_uint2(ka.z, ka.w) : cp == 2 ? make_uint2(kb.x, kb.y) : make_uint2(kb.z, kb.w);
             int32_t c0 = (int32_t)own.x, c1 = (int32_t)own.y;
             int32_t bar = jrow < M ? bar_of8(make_uint2(ka.x, ka.y), make_uint2(ka.z, ka.w), make_uint2(kb.x, kb.y), make_uint2(kb.z, kb.w)) : INT32_MIN;
             tc::mbar_wait(&S.acc_full[reg], (step_it >> 1) & 1);
