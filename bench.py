@@ -229,7 +229,8 @@ def roofline_record(kind, n_desc, pairs_done, kernel_s, engine, traffic_key):
     achieved = flop_per_pair * pairs_done / kernel_s / 1e12
     return {"bound": "tensor", "tensor_kind": "bf16 -> f32 (UTCHMMA)", "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s",
             "frac": achieved / peak_tf, "traffic": tj.get(traffic_key), "peak_source": f"bf16_tflops_sustained ({pk['_source']}, MEASURED_PEAKS.json)",
-            "work_per_pair": flop_per_pair, "kernel": "tc_match_pairs_kernel<sift>"}
+            "work_per_pair": flop_per_pair, "kernel": "sift_tc_match_pairs_kernel",
+            "note": "algorithmic FLOP: the kernel issues 2x this on the tensor cores (D and D^T, DESIGN.md section 7)"}
 
 
 def run_reference(args):
@@ -476,6 +477,21 @@ def run_single_gpu_workload(env, name, steps, warmup, e2e_steps, cpu_budget_s, o
                            "tensor_alu = same with sort-2 on the ALU pipe; tensor_v1 = round-1 kernel (F32 accumulators, 32-bit keys); "
                            "popc = orb_match_pairs_kernel (XOR + carry-save POPC). Bit-identical outputs (tests/test_gpu_orb*.py)")
         rec["engines"] = engines
+
+    if kind == "sift":
+        # A/B: the round-1 SIFT kernel (one MMA pass, REDUX column path, one query re-ranked at a time) on the same inputs
+        with eacham_b200.FeatureMatcherGpu(0.8, device=env.local_rank, sift_engine="tensor_v1") as m2:
+            m2.Upload(images)
+            m2.MatchPairsDevice(pairs)
+            m2.flush_l2(256 << 20)
+            m2.MatchPairsDevice(pairs)
+            ms1 = m2.timing()["kernel_ms"]
+            r2, b2 = m2.FetchResults()
+            same = bool(np.array_equal(r2["count"], res["count"]) and np.array_equal(r2["n_mutual"], res["n_mutual"]) and int(r2["count"].sum()) == len(b2))
+        rec["engines"] = {"tensor": {"value": value, "unit": "pairs/s", "steps": steps, "default": True},
+                          "tensor_v1": {"value": n_pairs / (ms1 * 1e-3), "unit": "pairs/s", "steps": 1, "default": False, "same_counts_as_default": same},
+                          "note": "tensor = sift_tc_match_pairs_kernel (D and D^T on the tensor cores, pruned thread-local scans, 16-query re-rank); "
+                                  "tensor_v1 = round-1 tc_match_pairs_kernel<sift>"}
 
     if with_match_api:
         # The reference-shaped per-call route driven the way apps/sfm/main.cpp:84-109 drives it: Match(d1, d2)

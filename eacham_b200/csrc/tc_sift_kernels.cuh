@@ -8,21 +8,28 @@
 //
 // What changed against the round-1 kernel (tc_match_kernels.cuh, kept behind EACHAM_CFG_SIFT_TC_V1 for A/B runs): that kernel was
 // bound by the ALU pipe (68 % busy, tensor pipe 19 %): every score went through a key build and a 3-instruction top-2 update for
-// its row, and through two warp-wide REDUX.MIN per column for the other direction. Here
+// its row, and through two warp-wide REDUX.MIN per column for the other direction; and a fifth of its time went into re-ranking
+// one query at a time (a full memory round trip each). Here
 //   * the score matrix of a (256 rows of `first`) x (128 rows of `second`) tile is computed TWICE by the tensor cores, once as
 //     D1 = A_half . B^T (TMEM lanes = rows of `first`) and once transposed as D2 = B . A_block^T (TMEM lanes = rows of `second`,
 //     one N = 256 MMA chain), from the same shared-memory operands. The tensor pipe has the headroom; in exchange BOTH directions
 //     become the same thread-local scan (a thread owns one TMEM lane = one query row) and all cross-lane work disappears;
-//   * the scan is pruned: a query's running second-best distance is a bar; eight scores are reduced with four 3-input integer
-//     minima and compared with the bar once, and only if some lane of the warp sees a score under its bar (__any_sync) are the
-//     eight keys built and inserted. The number of true insertions per query is O(log n); late in a sweep most groups of
-//     eight are skipped at 5 ALU instructions instead of 32;
-//   * the bar is the MERGED state of the query (all four column parts): each warp keeps tile-local candidates, hands them over
-//     through shared memory, and one of the quadrant's four warps (rotating) merges them into the query's state -- shared
-//     memory for the resident block of `first`, the per-CTA L2 scratch for `second` -- and publishes the new bar.
-// Keys, composites, tie-breaking (lower index wins) and everything after the sweep are those of the round-1 kernel, so
-// the candidates differ from it only where D1 and D2 round differently (never for bf16-exact, e.g. integer-valued, inputs), and
-// the match sets are exact either way (rerank_ratio_checked).
+//   * the scan is pruned: a query's running second-best distance is a bar; eight scores are reduced with three 3-input integer
+//     minima + one minimum and compared with the bar once, and only if some lane of the warp sees a score under its bar
+//     (__any_sync) are the eight keys built and inserted. True insertions per query are O(log n); measured, 32 % of the groups
+//     of eight take the slow path (that IS the insertion count: ~1.8 inserting lanes per slow group);
+//   * no barrier inside the sweep: each of the four column parts (warps) of a lane quadrant keeps its own running (best, second)
+//     keys -- registers for the resident rows, the per-CTA L2 scratch for the streamed ones -- publishes them (shared memory / the
+//     scratch) and derives its bar from ALL four parts' published keys (second smallest of the eight), read without
+//     synchronisation: a stale copy only means a higher bar, never a wrong result. The parts are merged once per row block /
+//     once per pair;
+//   * the exact re-rank handles sixteen queries per warp pass with twelve gathered rows in flight, a multi-value butterfly (one
+//     shuffle + one add per distance instead of five, same operand pairs, same bits) and the certainty logic once per sixteen
+//     queries (rerank_range).
+// Keys, composites and tie-breaking (lower index wins) are those of the round-1 kernel, so the candidates differ from it only where
+// D1 and D2 round differently (never for bf16-exact, e.g. integer-valued, inputs), and the match sets are exact either way
+// (tcm::rerank_ratio_checked's bound; the query's own norm is replaced by its image's maximum norm, still a bound).
+// Measured (200 images x 8192, 19,900 pairs): 29.1k pairs/s against 22.2k; tensor pipe 55 %, ALU 57 %.
 #pragma once
 #include <cstdint>
 #include <cstdio>
@@ -34,16 +41,6 @@
 #ifndef EACHAM_EXP
 #define EACHAM_EXP 0
 #endif
-#ifndef SIFT_BAR_EVERY
-#define SIFT_BAR_EVERY 4      // D1: the other parts' keys are re-read every this many tiles (power of two)
-#endif
-#ifndef SIFT_SUBGROUPS
-#define SIFT_SUBGROUPS 0      // a hit group of eight is narrowed to the sub-groups (3 + 3 + 2 scores) whose partial minimum is under a bar
-#endif
-#ifndef SIFT_TREE_BODY
-#define SIFT_TREE_BODY 0      // insertion of eight keys as a sort-2 / merge tree (1) or a chain of eight insertions (0)
-#endif
-
 namespace eacham {
 namespace tcs {
 
@@ -65,6 +62,7 @@ using tcm::kEmptyComp;
 using tcm::epi_bar;
 
 constexpr int kThreads = 64 + kEpiThreads;
+constexpr uint32_t kBarEvery = 4;                                   // D1: the other parts' keys are re-read every this many tiles (power of two)
 constexpr int kBStages = 3;
 constexpr int kAChunks = tc::kDataChunks + 2 * tc::kAugChunks;      // 20 K-chunks per row
 constexpr uint32_t kAChunkStride = 2 * tc::kChunkStride;            // resident block: the two 128-row halves side by side per K-chunk (4,096 B)
@@ -122,42 +120,14 @@ template <int kIdx0, int kOff>
 __device__ __forceinline__ void scan8(const uint32_t (&v)[16], uint32_t mask, int32_t& c0, int32_t& c1, int32_t& bar) {
     const int32_t x0 = (int32_t)v[kOff + 0], x1 = (int32_t)v[kOff + 1], x2 = (int32_t)v[kOff + 2], x3 = (int32_t)v[kOff + 3];
     const int32_t x4 = (int32_t)v[kOff + 4], x5 = (int32_t)v[kOff + 5], x6 = (int32_t)v[kOff + 6], x7 = (int32_t)v[kOff + 7];
-    const int32_t ga = min(min(x0, x1), x2), gb = min(min(x3, x4), x5), gc = min(x6, x7);
-    const int32_t mn = min(min(ga, gb), gc);
+    const int32_t mn = min(min(min(x0, x1), x2), min(min(min(x3, x4), x5), min(x6, x7)));      // four instructions (three 3-input minima)
     if (__any_sync(0xffffffffu, mn < bar)) {
-#if SIFT_SUBGROUPS
-        // second level: the three partial minima of the tree say which of the groups {0,1,2} {3,4,5} {6,7} hold the score(s) under a bar;
-        // typically one lane, one score -- so one group's insertions instead of all eight
-        if (__any_sync(0xffffffffu, ga < bar)) {
-            insert(key_of<kIdx0 + 0>(v[kOff + 0], mask), c0, c1); insert(key_of<kIdx0 + 1>(v[kOff + 1], mask), c0, c1);
-            insert(key_of<kIdx0 + 2>(v[kOff + 2], mask), c0, c1);
-        }
-        if (__any_sync(0xffffffffu, gb < bar)) {
-            insert(key_of<kIdx0 + 3>(v[kOff + 3], mask), c0, c1); insert(key_of<kIdx0 + 4>(v[kOff + 4], mask), c0, c1);
-            insert(key_of<kIdx0 + 5>(v[kOff + 5], mask), c0, c1);
-        }
-        if (__any_sync(0xffffffffu, gc < bar)) {
-            insert(key_of<kIdx0 + 6>(v[kOff + 6], mask), c0, c1); insert(key_of<kIdx0 + 7>(v[kOff + 7], mask), c0, c1);
-        }
-#elif SIFT_TREE_BODY
-        // top two of the eight keys by a sort-2 / merge tree (depth 7 instead of a 16-deep insertion chain), then into the state
-        const int32_t k0 = key_of<kIdx0 + 0>(v[kOff + 0], mask), k1 = key_of<kIdx0 + 1>(v[kOff + 1], mask);
-        const int32_t k2 = key_of<kIdx0 + 2>(v[kOff + 2], mask), k3 = key_of<kIdx0 + 3>(v[kOff + 3], mask);
-        const int32_t k4 = key_of<kIdx0 + 4>(v[kOff + 4], mask), k5 = key_of<kIdx0 + 5>(v[kOff + 5], mask);
-        const int32_t k6 = key_of<kIdx0 + 6>(v[kOff + 6], mask), k7 = key_of<kIdx0 + 7>(v[kOff + 7], mask);
-        const int32_t a0 = min(k0, k1), a1 = max(k0, k1), b0 = min(k2, k3), b1 = max(k2, k3);
-        const int32_t d0 = min(k4, k5), d1 = max(k4, k5), e0 = min(k6, k7), e1 = max(k6, k7);
-        const int32_t f0 = min(a0, b0), f1 = min(min(max(a0, b0), a1), b1);
-        const int32_t g0 = min(d0, e0), g1 = min(min(max(d0, e0), d1), e1);
-        const int32_t h0 = min(f0, g0), h1 = min(min(max(f0, g0), f1), g1);
-        c1 = min(min(max(c0, h0), c1), h1);
-        c0 = min(c0, h0);
-#else
+        // (measured alternatives, all slower or equal: a sort-2 / merge tree instead of this chain; narrowing to the sub-groups of the
+        //  min tree first; one vote per sixteen scores -- the sweep is bound by dependent-issue latency with four warps per scheduler)
         insert(key_of<kIdx0 + 0>(v[kOff + 0], mask), c0, c1); insert(key_of<kIdx0 + 1>(v[kOff + 1], mask), c0, c1);
         insert(key_of<kIdx0 + 2>(v[kOff + 2], mask), c0, c1); insert(key_of<kIdx0 + 3>(v[kOff + 3], mask), c0, c1);
         insert(key_of<kIdx0 + 4>(v[kOff + 4], mask), c0, c1); insert(key_of<kIdx0 + 5>(v[kOff + 5], mask), c0, c1);
         insert(key_of<kIdx0 + 6>(v[kOff + 6], mask), c0, c1); insert(key_of<kIdx0 + 7>(v[kOff + 7], mask), c0, c1);
-#endif
         bar = min(bar, (c1 + 255) & ~255);
     }
 }
@@ -306,7 +276,7 @@ __device__ __noinline__ uint32_t scan_block(SmemSift& S, uint32_t tmem, int q, i
             const uint32_t reg = step_it & 1;
             // bars from all four parts' published keys, every fourth tile (unsynchronised: stale only means a higher bar); in between
             // the bar only follows this part's own insertions. Padding rows never take part.
-            if ((bt & (SIFT_BAR_EVERY - 1u)) == (SIFT_BAR_EVERY > 1 ? 1u : 0u)) {
+            if ((bt & (kBarEvery - 1u)) == 1u) {
                 if (rv0) bar1[0] = min(bar1[0], bar_of8(S.share1[0][r0], S.share1[1][r0], S.share1[2][r0], S.share1[3][r0]));
                 if (rv1) bar1[1] = min(bar1[1], bar_of8(S.share1[0][r1], S.share1[1][r1], S.share1[2][r1], S.share1[3][r1]));
             }

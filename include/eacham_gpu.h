@@ -168,7 +168,8 @@ EACHAM_API int eacham_gpu_knn2(eacham_gpu_handle* h, int kind, const void* query
  *   strict unique minimum (true for ratio <= 1); a call with ratio > 1 runs on the packed-key XOR+POPC kernels instead.
  * F32X128: candidates are scored as a bf16 GEMM (exact for integer-valued rows, which is what cv::SIFT emits) and re-ranked in exact
  *   FP32. With |score - |a-b|^2/2| <= E for every train row, where
- *       E = delta (2 d1 + delta) / 2 + 2^-15 d1^2 / 2 + 2^-16 (|a|^2 + max|b|^2) / 2,   delta = 2^-9 (|a| + max|b|)
+ *       E = delta (2 d1 + delta) / 2 + 2^-15 d1^2 / 2 + 2^-16 (max|a|^2 + max|b|^2) / 2,   delta = 2^-9 (max|a| + max|b|)
+ *   (maxima over the rows of the query's / the train image)
  *   (first and last term 0 when both images are bf16-exact), the reference's ratio lies in [d0/d1, d0/sqrt(d1^2 - 4E)]. Only if that
  *   interval straddles `ratio` (or the best itself could be a non-candidate) is the query re-done by an exact FP32 scan over all train
  *   rows (eacham_gpu_timing.exact_fallbacks counts them). The returned match sets are therefore the exact matcher's for ANY float
