@@ -137,3 +137,29 @@ def test_sift_full_size_properties(matcher):
     inv = np.empty(n, np.int64); inv[perm] = np.arange(n)
     assert pm.n12 == n and pm.n21 == n and pm.n_mutual == n
     assert np.array_equal(pm.matches[:, 0], np.arange(n)) and np.array_equal(pm.matches[:, 1], inv)
+
+
+@pytest.mark.parametrize("sizes", [(1536, 1300, 257, 129), (8, 3000, 383, 1), (2049, 2, 640, 511)])
+def test_sift_engines_agree_on_ragged_sizes(sizes):
+    """The default engine (D and D^T on the tensor cores, pruned scans, tc_sift_kernels.cuh), the round-1 tensor kernel
+    (EACHAM_CFG_SIFT_TC_V1) and the all-FP32 kernels return the same pairs on integer-valued rows of ragged sizes: partial last row
+    blocks (one resident half only), partial last tiles, fewer rows than a tile, single rows; both roles of every image."""
+    import eacham_b200
+    from eacham_b200 import synth
+    rng = np.random.default_rng(sum(sizes))
+    pool = synth.sift_image_set(1, 6000, seed=17, pool=6000)[0]
+    imgs = [np.ascontiguousarray(pool[rng.choice(pool.shape[0], n, replace=False)]) for n in sizes]
+    pairs = [(i, j) for i in range(len(imgs)) for j in range(len(imgs)) if i != j]
+    out = {}
+    for engine in ("tensor", "tensor_v1", "fp32"):
+        with eacham_b200.FeatureMatcherGpu(0.8, sift_engine=engine, min_dir=0, min_mutual=0) as m:
+            m.Upload(imgs)
+            out[engine] = m.MatchPairs(pairs, emit_all=True)
+            if engine == "tensor":                  # the per-call route runs the same kernel in single-direction mode
+                for i, j in pairs[:4]:
+                    assert len(m.Match(imgs[i], imgs[j])) == _ref_pair(imgs[i], imgs[j], min_dir=0, min_mutual=0)["n12"], (i, j)
+    for a, b, c, (i, j) in zip(out["tensor"], out["tensor_v1"], out["fp32"], pairs):
+        assert (a.n12, a.n21, a.n_mutual) == (b.n12, b.n21, b.n_mutual) == (c.n12, c.n21, c.n_mutual), (i, j)
+        assert np.array_equal(a.matches, b.matches) and np.array_equal(a.matches, c.matches), (i, j)
+        ref = _ref_pair(imgs[i], imgs[j], min_dir=0, min_mutual=0)
+        assert (a.n12, a.n21, a.n_mutual) == (ref["n12"], ref["n21"], ref["n_mutual"]), (i, j)
