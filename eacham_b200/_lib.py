@@ -56,11 +56,11 @@ RESULT_DTYPE = [("n12", "<u4"), ("n21", "<u4"), ("n_mutual", "<u4"), ("flags", "
 # every symbol include/eacham_gpu.h declares (tests check the header against this list and the .so)
 SYMBOLS = [
     "eacham_gpu_abi_version", "eacham_gpu_device_count", "eacham_gpu_last_error", "eacham_gpu_default_opts",
-    "eacham_gpu_create", "eacham_gpu_destroy", "eacham_gpu_set_descriptors", "eacham_gpu_reserve", "eacham_gpu_commit",
+    "eacham_gpu_create", "eacham_gpu_destroy", "eacham_gpu_set_descriptors", "eacham_gpu_set_descriptors_batch", "eacham_gpu_reserve", "eacham_gpu_commit",
     "eacham_gpu_clear", "eacham_gpu_arena", "eacham_gpu_image_info", "eacham_gpu_match", "eacham_gpu_knn2",
     "eacham_gpu_match_pairs", "eacham_gpu_match_pairs_device", "eacham_gpu_fetch_results", "eacham_gpu_device_results", "eacham_gpu_last_timing",
     "eacham_gpu_flush_l2",
-    "eacham_gpu_create_multi", "eacham_gpu_destroy_multi", "eacham_gpu_multi_device_count", "eacham_gpu_multi_set_descriptors",
+    "eacham_gpu_create_multi", "eacham_gpu_destroy_multi", "eacham_gpu_multi_device_count", "eacham_gpu_multi_set_descriptors", "eacham_gpu_multi_set_descriptors_batch",
     "eacham_gpu_multi_clear", "eacham_gpu_multi_commit", "eacham_gpu_multi_match_pairs", "eacham_gpu_multi_last_timing",
     "eacham_gpu_host_alloc", "eacham_gpu_host_free", "eacham_gpu_debug_pair_knn2", "eacham_gpu_set_keypoints", "eacham_gpu_verify_pairs",
 ]
@@ -94,6 +94,7 @@ def load() -> ctypes.CDLL:
     lib.eacham_gpu_destroy.argtypes = [vp]
     lib.eacham_gpu_destroy.restype = None
     lib.eacham_gpu_set_descriptors.argtypes = [vp, u32, i32, vp, u32, sz]
+    lib.eacham_gpu_set_descriptors_batch.argtypes = [vp, u32, u32, i32, vp, vp, vp]
     lib.eacham_gpu_reserve.argtypes = [vp, u32, i32, u32]
     lib.eacham_gpu_commit.argtypes = [vp]
     lib.eacham_gpu_clear.argtypes = [vp]
@@ -116,6 +117,7 @@ def load() -> ctypes.CDLL:
     lib.eacham_gpu_multi_device_count.argtypes = [vp]
     lib.eacham_gpu_multi_device_count.restype = u32
     lib.eacham_gpu_multi_set_descriptors.argtypes = [vp, u32, i32, vp, u32, sz]
+    lib.eacham_gpu_multi_set_descriptors_batch.argtypes = [vp, u32, u32, i32, vp, vp, vp]
     lib.eacham_gpu_multi_clear.argtypes = [vp]
     lib.eacham_gpu_multi_commit.argtypes = [vp]
     lib.eacham_gpu_multi_match_pairs.argtypes = [vp, vp, sz, P(MatchOpts), vp, vp, sz, P(sz)]

@@ -13,6 +13,7 @@
 #include <mutex>
 #include <new>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include <cuda_runtime.h>
@@ -314,6 +315,58 @@ int eacham_gpu_set_descriptors(eacham_gpu_handle* h, uint32_t image_id, int kind
     if (row_stride_bytes == rb) memcpy(dst, data, (size_t)rows * rb);
     else for (uint32_t r = 0; r < rows; ++r) memcpy(dst + (size_t)r * rb, (const uint8_t*)data + (size_t)r * row_stride_bytes, rb);
     im.has_data = true; im.reserved = false;
+    h->any_data = true;
+    return EACHAM_OK;
+}
+
+// Many images in one call (image ids first_id .. first_id + n - 1): arguments are validated up front, the staging buffer grows once, and
+// the copies into it run on a few host threads (a single memcpy stream fills pinned memory at ~10 GB/s, far below the PCIe link it feeds).
+int eacham_gpu_set_descriptors_batch(eacham_gpu_handle* h, uint32_t first_id, uint32_t n, int kind, const void* const* data, const uint32_t* rows,
+                                     const size_t* row_stride_bytes) {
+    if (!h) return fail(EACHAM_ERR_INVALID_ARG, "null handle");
+    if (kind != EACHAM_KIND_ORB256 && kind != EACHAM_KIND_F32X128) return fail(EACHAM_ERR_INVALID_ARG, "unknown descriptor kind %d", kind);
+    if (n == 0) return EACHAM_OK;
+    if (!data || !rows) return fail(EACHAM_ERR_INVALID_ARG, "null array");
+    if ((uint64_t)first_id + n > (1u << 26)) return fail(EACHAM_ERR_INVALID_ARG, "image ids %u .. +%u out of range", first_id, n);
+    const size_t rb = row_bytes(kind);
+    size_t total = 0;
+    for (uint32_t i = 0; i < n; ++i) {
+        if (rows[i] > 65535u) return fail(EACHAM_ERR_TOO_LARGE, "image %u has %u descriptors; at most 65535 are supported", first_id + i, rows[i]);
+        if (rows[i] > 0 && !data[i]) return fail(EACHAM_ERR_INVALID_ARG, "null descriptor pointer for image %u", first_id + i);
+        if (rows[i] > 0 && row_stride_bytes && row_stride_bytes[i] < rb)
+            return fail(EACHAM_ERR_INVALID_ARG, "image %u: row stride %zu < row size %zu", first_id + i, row_stride_bytes[i], rb);
+        total += align_up((size_t)rows[i] * rb, kAlign);
+    }
+    std::lock_guard<std::mutex> lk(h->mu);
+    DeviceGuard g(h->device);
+    int rc = ensure_staging(h, align_up(h->staging_used, kAlign) + total + kAlign);      // one growth instead of one per image
+    if (rc) return rc;
+    for (uint32_t i = 0; i < n; ++i)
+        if ((rc = place_image(h, first_id + i, kind, rows[i], /*backed=*/true))) return rc;
+    auto copy_range = [&](uint32_t lo, uint32_t hi) {
+        for (uint32_t i = lo; i < hi; ++i) {
+            const ImageHost& im = h->images[first_id + i];
+            uint8_t* dst = h->staging + im.offset;
+            const size_t stride = row_stride_bytes ? row_stride_bytes[i] : rb;
+            if (stride == rb) memcpy(dst, data[i], (size_t)rows[i] * rb);
+            else for (uint32_t r = 0; r < rows[i]; ++r) memcpy(dst + (size_t)r * rb, (const uint8_t*)data[i] + (size_t)r * stride, rb);
+        }
+    };
+    const unsigned hw = std::max(1u, std::thread::hardware_concurrency());
+    const unsigned workers = (unsigned)std::min<size_t>(std::min(hw, 8u), std::max<size_t>(1, total >> 22));      // one per 4 MiB, at most 8
+    if (workers <= 1) copy_range(0, n);
+    else {
+        // contiguous ranges of about equal bytes
+        std::vector<std::thread> pool;
+        uint32_t lo = 0;
+        size_t acc = 0, share = (total + workers - 1) / workers;
+        for (uint32_t i = 0; i < n; ++i) {
+            acc += align_up((size_t)rows[i] * rb, kAlign);
+            if (acc >= share || i + 1 == n) { pool.emplace_back(copy_range, lo, i + 1); lo = i + 1; acc = 0; }
+        }
+        for (std::thread& t : pool) t.join();
+    }
+    for (uint32_t i = 0; i < n; ++i) { ImageHost& im = h->images[first_id + i]; im.has_data = true; im.reserved = false; }
     h->any_data = true;
     return EACHAM_OK;
 }

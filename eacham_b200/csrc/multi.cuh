@@ -147,6 +147,13 @@ int eacham_gpu_multi_set_descriptors(eacham_gpu_multi* m, uint32_t image_id, int
     return eacham_gpu_set_descriptors(m->dev[0], image_id, kind, data, rows, row_stride_bytes);
 }
 
+int eacham_gpu_multi_set_descriptors_batch(eacham_gpu_multi* m, uint32_t first_id, uint32_t n, int kind, const void* const* data, const uint32_t* rows,
+                                           const size_t* row_stride_bytes) {
+    if (!m) return fail(EACHAM_ERR_INVALID_ARG, "null handle");
+    std::lock_guard<std::mutex> lk(m->mu);
+    return eacham_gpu_set_descriptors_batch(m->dev[0], first_id, n, kind, data, rows, row_stride_bytes);
+}
+
 int eacham_gpu_multi_clear(eacham_gpu_multi* m) {
     if (!m) return fail(EACHAM_ERR_INVALID_ARG, "null handle");
     std::lock_guard<std::mutex> lk(m->mu);

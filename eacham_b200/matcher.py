@@ -51,6 +51,31 @@ class PairMatches:
         return {int(b): int(a) for a, b in self.matches}
 
 
+def _upload_batched(fn, handle, descriptors: Sequence[np.ndarray]) -> None:
+    """Runs of consecutive images of one kind go through one batch call each (pointer / row count / stride arrays)."""
+    n = len(descriptors)
+    keep = []                                   # the (possibly converted) arrays must outlive the call
+    ptrs = (ctypes.c_void_p * max(n, 1))()
+    rows = np.zeros(max(n, 1), np.uint32)
+    strides = (ctypes.c_size_t * max(n, 1))()
+    kinds = []
+    for i, d in enumerate(descriptors):
+        kinds.append(_kind_of(d))
+        d, p, r, s = _rows_ptr(d)
+        keep.append(d)
+        ptrs[i] = p.value if isinstance(p, ctypes.c_void_p) else p
+        rows[i] = r
+        strides[i] = s
+    i = 0
+    while i < n:
+        j = i
+        while j < n and kinds[j] == kinds[i]:
+            j += 1
+        L.check(fn(handle, i, j - i, kinds[i], ctypes.byref(ptrs, i * ctypes.sizeof(ctypes.c_void_p)),
+                   rows[i:].ctypes.data_as(ctypes.c_void_p), ctypes.byref(strides, i * ctypes.sizeof(ctypes.c_size_t))))
+        i = j
+
+
 class FeatureMatcherGpu:
     """B200 matcher with the reference's ``FeatureMatcherFlann`` shape.
 
@@ -154,10 +179,9 @@ class FeatureMatcherGpu:
         L.check(self._lib.eacham_gpu_clear(self._h))
 
     def Upload(self, descriptors: Sequence[np.ndarray]) -> None:
-        """set_descriptors for image ids 0..n-1 followed by one commit (one H2D copy)."""
+        """All images (ids 0..n-1) staged by one set_descriptors_batch call per descriptor kind, followed by one commit (one H2D copy)."""
         self.Clear()
-        for i, d in enumerate(descriptors):
-            self.SetDescriptors(i, d)
+        _upload_batched(self._lib.eacham_gpu_set_descriptors_batch, self._h, descriptors)
         self.Commit()
 
     def arena(self) -> Tuple[int, int]:

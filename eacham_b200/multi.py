@@ -13,7 +13,7 @@ from typing import Dict, List, Optional, Sequence
 import numpy as np
 
 from . import _lib as L
-from .matcher import PairMatches, _kind_of, _rows_ptr
+from .matcher import PairMatches, _kind_of, _rows_ptr, _upload_batched
 
 
 class PinnedBuffer:
@@ -86,10 +86,7 @@ class MultiGpuMatcher:
     def Upload(self, descriptors: Sequence[np.ndarray]) -> None:
         """clear + set_descriptors for ids 0..n-1 + commit: one H2D copy to devices[0], one NCCL broadcast."""
         L.check(self._lib.eacham_gpu_multi_clear(self._h))
-        for i, d in enumerate(descriptors):
-            kind = _kind_of(d)
-            d, p, n, s = _rows_ptr(d)
-            L.check(self._lib.eacham_gpu_multi_set_descriptors(self._h, i, kind, p, n, s))
+        _upload_batched(self._lib.eacham_gpu_multi_set_descriptors_batch, self._h, descriptors)
         L.check(self._lib.eacham_gpu_multi_commit(self._h))
 
     def _pinned(self, which: str, n: int, dtype) -> PinnedBuffer:

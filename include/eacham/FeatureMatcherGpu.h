@@ -121,6 +121,30 @@ public:
         return matchesPair;
     }
 
+    // all images through one batched staging call per run of equal descriptor kind (several host threads copy into pinned memory)
+    template <typename Mat, typename Fn>
+    static void Stage(const std::vector<Mat>& descriptors, Fn&& stage)
+    {
+        const size_t n = descriptors.size();
+        std::vector<const void*> data(n);
+        std::vector<uint32_t> rows(n);
+        std::vector<size_t> steps(n);
+        for (size_t k = 0; k < n; ++k)
+        {
+            data[k] = descriptors[k].data;
+            rows[k] = static_cast<uint32_t>(descriptors[k].rows);
+            steps[k] = Step(descriptors[k]);
+        }
+        for (size_t i = 0; i < n;)
+        {
+            size_t j = i;
+            const int kind = KindOf(descriptors[i]);
+            while (j < n && KindOf(descriptors[j]) == kind) ++j;
+            Check(stage(static_cast<uint32_t>(i), static_cast<uint32_t>(j - i), kind, data.data() + i, rows.data() + i, steps.data() + i));
+            i = j;
+        }
+    }
+
     template <typename Mat>
     std::vector<PairMatches> MatchPairsAny(const std::vector<Mat>& descriptors,
                                            const std::vector<std::pair<unsigned, unsigned>>& pairs)
@@ -133,9 +157,8 @@ public:
         if (multi != nullptr)
         {
             Check(eacham_gpu_multi_clear(multi));
-            for (size_t k = 0; k < descriptors.size(); ++k)
-                Check(eacham_gpu_multi_set_descriptors(multi, static_cast<uint32_t>(k), KindOf(descriptors[k]), descriptors[k].data,
-                                                       static_cast<uint32_t>(descriptors[k].rows), Step(descriptors[k])));
+            Stage(descriptors, [this](uint32_t first, uint32_t n, int kind, const void* const* d, const uint32_t* r, const size_t* s)
+                  { return eacham_gpu_multi_set_descriptors_batch(multi, first, n, kind, d, r, s); });
             Check(eacham_gpu_multi_commit(multi));
             PinnedMatches buf(guess);       // page-locked: every device copies its shard at full PCIe rate
             int rc = eacham_gpu_multi_match_pairs(multi, p.data(), p.size(), &opts, res.data(), buf.p, buf.n, &used);
@@ -148,9 +171,8 @@ public:
             return Unpack(pairs, res, buf.p);
         }
         Check(eacham_gpu_clear(handle));
-        for (size_t k = 0; k < descriptors.size(); ++k)
-            Check(eacham_gpu_set_descriptors(handle, static_cast<uint32_t>(k), KindOf(descriptors[k]), descriptors[k].data,
-                                             static_cast<uint32_t>(descriptors[k].rows), Step(descriptors[k])));
+        Stage(descriptors, [this](uint32_t first, uint32_t n, int kind, const void* const* d, const uint32_t* r, const size_t* s)
+              { return eacham_gpu_set_descriptors_batch(handle, first, n, kind, d, r, s); });
         Check(eacham_gpu_commit(handle));
         std::vector<eacham_match_t> buf(guess);
         int rc = eacham_gpu_match_pairs(handle, p.data(), p.size(), &opts, res.data(), buf.data(), buf.size(), &used);

@@ -134,6 +134,11 @@ EACHAM_API void eacham_gpu_destroy(eacham_gpu_handle* h);
  * row_stride_bytes >= 32 (ORB256) or >= 512 (F32X128): cv::Mat::step of a possibly non-continuous Mat. */
 EACHAM_API int eacham_gpu_set_descriptors(eacham_gpu_handle* h, uint32_t image_id, int kind, const void* data, uint32_t rows,
                                size_t row_stride_bytes);
+/* The same for image ids first_id .. first_id + n - 1 in one call: data[i] / rows[i] / row_stride_bytes[i] describe image first_id + i
+ * (row_stride_bytes may be NULL = dense rows). Arguments are validated before anything is staged; the copies into the pinned staging
+ * buffer run on several host threads. What a loader that already holds every Node's descriptors (apps/sfm/main.cpp:72-79) should call. */
+EACHAM_API int eacham_gpu_set_descriptors_batch(eacham_gpu_handle* h, uint32_t first_id, uint32_t n, int kind, const void* const* data,
+                                     const uint32_t* rows, const size_t* row_stride_bytes);
 /* Declare an image's shape without data (ranks that receive the arena by broadcast). */
 EACHAM_API int eacham_gpu_reserve(eacham_gpu_handle* h, uint32_t image_id, int kind, uint32_t rows);
 /* Lay the staged images out in the device arena and upload whatever data was staged (one H2D copy). */
@@ -227,6 +232,8 @@ EACHAM_API void eacham_gpu_destroy_multi(eacham_gpu_multi* m);
 EACHAM_API uint32_t eacham_gpu_multi_device_count(eacham_gpu_multi* m);
 EACHAM_API int eacham_gpu_multi_set_descriptors(eacham_gpu_multi* m, uint32_t image_id, int kind, const void* data, uint32_t rows,
                                                 size_t row_stride_bytes);
+EACHAM_API int eacham_gpu_multi_set_descriptors_batch(eacham_gpu_multi* m, uint32_t first_id, uint32_t n, int kind, const void* const* data,
+                                           const uint32_t* rows, const size_t* row_stride_bytes);
 EACHAM_API int eacham_gpu_multi_clear(eacham_gpu_multi* m);
 EACHAM_API int eacham_gpu_multi_commit(eacham_gpu_multi* m);
 EACHAM_API int eacham_gpu_multi_match_pairs(eacham_gpu_multi* m, const eacham_pair_t* pairs, size_t n_pairs, const eacham_match_opts* opts,

@@ -292,3 +292,44 @@ def test_match_route_cache_and_concurrency(kind):
                 assert m.Match(imgs[1], imgs[0]) == O.c_match(imgs[1], imgs[0])
                 imgs[0][:] = old
                 assert m.Match(imgs[0], imgs[1]) == want[(0, 1)]
+
+
+def test_batched_staging_equals_per_image_staging():
+    """eacham_gpu_set_descriptors_batch (what Upload uses; several host threads copy into the pinned staging buffer) lays out the same arena as
+    one eacham_gpu_set_descriptors call per image: ragged, empty and strided images, > 4 MiB in total so that more than one worker runs;
+    and its argument errors are reported before anything is staged."""
+    import ctypes
+    import eacham_b200
+    from eacham_b200 import _lib as L
+    rng = np.random.default_rng(5)
+    pool = rng.integers(0, 256, (30000, 40), dtype=np.uint8)
+    imgs = []
+    for k in range(160):
+        n = int(rng.integers(0, 2049)) if k % 17 else 0
+        rows = pool[rng.choice(pool.shape[0], n, replace=False)]
+        imgs.append(rows[:, 4:36] if k % 3 == 0 else np.ascontiguousarray(rows[:, :32]))       # every third one strided (step 40)
+    pairs = [(i, j) for i in range(len(imgs)) for j in range(i + 1, min(i + 4, len(imgs)))]
+    with eacham_b200.FeatureMatcherGpu(0.8) as a, eacham_b200.FeatureMatcherGpu(0.8) as b:
+        a.Upload(imgs)                                              # batched
+        for i, d in enumerate(imgs):
+            b.SetDescriptors(i, d)                                  # one call per image
+        b.Commit()
+        assert a.arena()[1] == b.arena()[1]
+        ra, rb = a.MatchPairs(pairs, emit_all=True), b.MatchPairs(pairs, emit_all=True)
+        for x, y in zip(ra, rb):
+            assert (x.n12, x.n21, x.n_mutual, x.gated, x.connected) == (y.n12, y.n21, y.n_mutual, y.gated, y.connected)
+            assert np.array_equal(x.matches, y.matches)
+        # errors: nothing staged, the committed batch still answers
+        ptrs = (ctypes.c_void_p * 2)(imgs[1].ctypes.data, None)
+        rows = np.array([imgs[1].shape[0], 5], np.uint32)
+        with pytest.raises(L.EachamGpuError) as e:
+            L.check(a._lib.eacham_gpu_set_descriptors_batch(a._h, 0, 2, L.KIND_ORB256, ptrs, rows.ctypes.data_as(ctypes.c_void_p), None))
+        assert e.value.code == L.ERR_INVALID_ARG
+        rows[1] = 70000
+        ptrs[1] = imgs[1].ctypes.data
+        with pytest.raises(L.EachamGpuError) as e:
+            L.check(a._lib.eacham_gpu_set_descriptors_batch(a._h, 0, 2, L.KIND_ORB256, ptrs, rows.ctypes.data_as(ctypes.c_void_p), None))
+        assert e.value.code == L.ERR_TOO_LARGE
+        again = a.MatchPairs(pairs[:8], emit_all=True)
+        for x, y in zip(again, ra[:8]):
+            assert np.array_equal(x.matches, y.matches)
