@@ -163,3 +163,21 @@ def test_sift_engines_agree_on_ragged_sizes(sizes):
         assert np.array_equal(a.matches, b.matches) and np.array_equal(a.matches, c.matches), (i, j)
         ref = _ref_pair(imgs[i], imgs[j], min_dir=0, min_mutual=0)
         assert (a.n12, a.n21, a.n_mutual) == (ref["n12"], ref["n21"], ref["n_mutual"]), (i, j)
+
+
+def test_sift_engines_agree_on_large_images():
+    """20,000 x 9,000 rows: more than 128 tiles and more than 64 row blocks per pair (tile / row-block ids beyond one byte), partial
+    last block and tile; the default engine, the round-1 tensor kernel and the all-FP32 kernels return the same pair."""
+    import eacham_b200
+    from eacham_b200 import synth
+    a, b = synth.sift_image_set(2, 20000, seed=21, pool=60000, share=0.3)
+    b = np.ascontiguousarray(b[:9000])
+    out = {}
+    for engine in ("tensor", "tensor_v1", "fp32"):
+        with eacham_b200.FeatureMatcherGpu(0.8, sift_engine=engine) as m:
+            m.Upload([a, b])
+            out[engine] = m.MatchPairs([(0, 1), (1, 0)], emit_all=True)
+    for x, y, z in zip(out["tensor"], out["tensor_v1"], out["fp32"]):
+        assert x.n12 > 100 and x.n21 > 100
+        assert (x.n12, x.n21, x.n_mutual) == (y.n12, y.n21, y.n_mutual) == (z.n12, z.n21, z.n_mutual)
+        assert np.array_equal(x.matches, y.matches) and np.array_equal(x.matches, z.matches)
