@@ -80,6 +80,12 @@ __host__ __device__ constexpr uint64_t make_smem_desc_base(uint32_t lbo_bytes, u
 __device__ __forceinline__ uint64_t smem_desc(uint64_t base, uint32_t smem_addr) {
     return base | (uint64_t)((smem_addr >> 4) & 0x3FFF);
 }
+// a descriptor from its two words (low word: address field + LBO, high word: SBO + version; see above)
+__device__ __forceinline__ uint64_t desc_from(uint32_t lo, uint32_t hi) {
+    uint64_t d;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(d) : "r"(lo), "r"(hi));
+    return d;
+}
 __host__ __device__ constexpr uint32_t make_idesc_bf16_f32(uint32_t m, uint32_t n, bool negate_a) {
     return (1u << 4) | (1u << 7) | (1u << 10) | ((negate_a ? 1u : 0u) << 13) | ((n >> 3) << 17) | ((m >> 4) << 24);
 }

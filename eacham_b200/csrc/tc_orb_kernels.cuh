@@ -227,6 +227,11 @@ __global__ void __launch_bounds__(kThreads, 1) orb_tc_match_pairs_kernel(const P
         {
             const uint64_t dbase = tc::make_smem_desc_base(tc::kLBO, tc::kSBO);
             const uint32_t idesc = tc::make_idesc_e4m3(128, 128, true, /*d_f32=*/false);
+            const uint32_t desc_hi = (uint32_t)(dbase >> 32);
+            const uint32_t a_lo0 = (uint32_t)tc::smem_desc(dbase, tc::smem_u32(S.a[0])), a_lo1 = (uint32_t)tc::smem_desc(dbase, tc::smem_u32(S.a[1]));
+            const uint32_t b_lo0 = (uint32_t)tc::smem_desc(dbase, tc::smem_u32(S.b[0])), b_lo1 = (uint32_t)tc::smem_desc(dbase, tc::smem_u32(S.b[1]));
+            constexpr uint32_t kDescStep = (2 * tc::kChunkStride) >> 4;      // one K-step = two 16-byte K-chunks, in the descriptor's 16-byte units
+            static_assert(kBStages == 2, "two B stages assumed by the descriptor selection");
             uint32_t b_it = 0, a_it = 0, acc_it = 0;
             for (uint32_t k = 0;; ++k) {
                 const uint32_t rs = k % kRing;
@@ -252,15 +257,18 @@ __global__ void __launch_bounds__(kThreads, 1) orb_tc_match_pairs_kernel(const P
                         if (lane == 0) EACHAM_TRACE(1, acc_it, 2);
                         tc::tc_fence_after();
                         if (tc::elect_one()) {
-                            const uint32_t b_addr = tc::smem_u32(S.b[st]);
-                            for (uint32_t h = 0; h < nh; ++h) {
-                                const uint32_t a_addr = tc::smem_u32(S.a[h]);
-                                const uint32_t d = tmem + as * 256 + h * 128;
+                            // descriptors = a base built once per kernel + a constant per K-step (the address field counts 16-byte units and
+                            // shared-memory addresses stay below 2^18, so the 14-bit field never carries): the issuing warp shares its scheduler
+                            // with four epilogue warps, and rebuilding 36 descriptors per tile from addresses cost ~135 of its issue slots
+                            const uint32_t b_lo = st ? b_lo1 : b_lo0;
 #pragma unroll
-                                for (int ks = 0; ks < tc::kKSteps; ++ks) {
-                                    const uint64_t da = tc::smem_desc(dbase, a_addr + ks * 2 * tc::kChunkStride);
-                                    const uint64_t db = tc::smem_desc(dbase, b_addr + ks * 2 * tc::kChunkStride);
-                                    tc::mma_f8(d, da, db, idesc, ks > 0);
+                            for (uint32_t h = 0; h < 2; ++h) {
+                                if (h < nh) {
+                                    const uint32_t a_lo = h ? a_lo1 : a_lo0;
+                                    const uint32_t d = tmem + as * 256 + h * 128;
+#pragma unroll
+                                    for (int ks = 0; ks < tc::kKSteps; ++ks)
+                                        tc::mma_f8(d, tc::desc_from(a_lo + ks * kDescStep, desc_hi), tc::desc_from(b_lo + ks * kDescStep, desc_hi), idesc, ks > 0);
                                 }
                             }
                             tc::mma_commit(&S.b_empty[st]);      // B stage reusable once these MMAs have read it

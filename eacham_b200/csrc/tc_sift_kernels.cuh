@@ -429,7 +429,14 @@ __global__ void __launch_bounds__(kThreads, 1) sift_tc_match_pairs_kernel(const 
         const uint64_t dbase_a = tc::make_smem_desc_base(kAChunkStride, tc::kSBO);
         const uint64_t dbase_b = tc::make_smem_desc_base(tc::kLBO, tc::kSBO);
         const uint32_t idesc128 = tc::make_idesc_bf16_f32(128, 128, true), idesc256 = tc::make_idesc_bf16_f32(128, 256, true);
-        const uint32_t a_addr = tc::smem_u32(S.a);
+        // descriptors = a base built once + a constant per K-chunk (the address field counts 16-byte units; shared-memory addresses stay
+        // below 2^18, so the 14-bit field never carries): rebuilding them from addresses per tile cost the issuing warp ~200 issue slots
+        const uint32_t hi_a = (uint32_t)(dbase_a >> 32), hi_b = (uint32_t)(dbase_b >> 32);
+        const uint32_t a_lo = (uint32_t)tc::smem_desc(dbase_a, tc::smem_u32(S.a));
+        const uint32_t b_lo0 = (uint32_t)tc::smem_desc(dbase_b, tc::smem_u32(S.b[0])), b_lo1 = (uint32_t)tc::smem_desc(dbase_b, tc::smem_u32(S.b[1])),
+                       b_lo2 = (uint32_t)tc::smem_desc(dbase_b, tc::smem_u32(S.b[2]));
+        static_assert(kBStages == 3, "three B stages assumed by the descriptor selection");
+        constexpr uint32_t kStepA = kAChunkStride >> 4, kStepB = tc::kChunkStride >> 4, kHalfA = tc::kChunkStride >> 4;      // per K-chunk / per resident half
         uint32_t b_it = 0, a_it = 0, step_it = 0;
         for (uint32_t wk = blockIdx.x; wk < p.n_pairs; wk += gridDim.x) {
             const uint32_t pi = p.single_dir ? wk : p.order[wk];
@@ -442,7 +449,7 @@ __global__ void __launch_bounds__(kThreads, 1) sift_tc_match_pairs_kernel(const 
                 tc::mbar_wait(&S.a_full, a_it & 1);
                 for (uint32_t bt = 0; bt < nbt; ++bt, ++b_it) {
                     const uint32_t st = b_it % kBStages;
-                    const uint32_t b_addr = tc::smem_u32(S.b[st]);
+                    const uint32_t b_lo = st == 0 ? b_lo0 : st == 1 ? b_lo1 : b_lo2;
                     tc::mbar_wait(&S.b_full[st], (b_it / kBStages) & 1);
                     SIFT_TRACE(2, b_it, 0);
                     {   // D1: rows of `first` in the TMEM lanes
@@ -451,14 +458,15 @@ __global__ void __launch_bounds__(kThreads, 1) sift_tc_match_pairs_kernel(const 
                         tc::tc_fence_after();
                         SIFT_TRACE(2, b_it, 1);
                         if (tc::elect_one()) {
-                            for (uint32_t h = 0; h < nh; ++h) {
-                                const uint32_t d = tmem + reg * 256 + h * 128;
 #pragma unroll
-                                for (int ks = 0; ks < tc::kKSteps; ++ks) {
-                                    const int ca = ks < 8 ? 2 * ks : kAugChunkM, cb = ks < 8 ? 2 * ks : kAugChunkN;
-                                    const uint64_t da = tc::smem_desc(dbase_a, a_addr + ca * kAChunkStride + h * tc::kChunkStride);
-                                    const uint64_t db = tc::smem_desc(dbase_b, b_addr + cb * tc::kChunkStride);
-                                    tc::mma_bf16(d, da, db, idesc128, ks > 0);
+                            for (uint32_t h = 0; h < 2; ++h) {
+                                if (h < nh) {
+                                    const uint32_t d = tmem + reg * 256 + h * 128;
+#pragma unroll
+                                    for (int ks = 0; ks < tc::kKSteps; ++ks) {
+                                        const int ca = ks < 8 ? 2 * ks : kAugChunkM, cb = ks < 8 ? 2 * ks : kAugChunkN;
+                                        tc::mma_bf16(d, tc::desc_from(a_lo + ca * kStepA + h * kHalfA, hi_a), tc::desc_from(b_lo + cb * kStepB, hi_b), idesc128, ks > 0);
+                                    }
                                 }
                             }
                             if (!both) tc::mma_commit(&S.b_empty[st]);
@@ -477,9 +485,7 @@ __global__ void __launch_bounds__(kThreads, 1) sift_tc_match_pairs_kernel(const 
 #pragma unroll
                             for (int ks = 0; ks < tc::kKSteps; ++ks) {
                                 const int cm = ks < 8 ? 2 * ks : kAugChunkM, cn = ks < 8 ? 2 * ks : kAugChunkN;
-                                const uint64_t dm = tc::smem_desc(dbase_b, b_addr + cm * tc::kChunkStride);
-                                const uint64_t dn = tc::smem_desc(dbase_a, a_addr + cn * kAChunkStride);
-                                tc::mma_bf16(d, dm, dn, nh == 2 ? idesc256 : idesc128, ks > 0);
+                                tc::mma_bf16(d, tc::desc_from(b_lo + cm * kStepB, hi_b), tc::desc_from(a_lo + cn * kStepA, hi_a), nh == 2 ? idesc256 : idesc128, ks > 0);
                             }
                             tc::mma_commit(&S.b_empty[st]);
                             tc::mma_commit(&S.acc_full[reg]);
