@@ -215,7 +215,7 @@ constexpr int32_t kEmptyKeyTc = 0x7F7FFF00;
 constexpr long long kEmptyComp = ((long long)0x7F7FFF << 32) | 0xFFFFFFFFll;
 
 __host__ __device__ inline size_t tc_scratch_bytes_per_cta(uint32_t rows_cap, uint32_t cols_cap) {
-    return (size_t)cols_cap * 64 + (size_t)rows_cap * 4 + (size_t)cols_cap * 4;      // column state (<= 64 B per column: tc_sift_kernels.cuh) + m12 + m21
+    return (size_t)cols_cap * 96 + (size_t)rows_cap * 4 + (size_t)cols_cap * 4;      // column state (<= 96 B per column: tc_sift_kernels.cuh) + m12 + m21
 }
 
 struct SmemTc {

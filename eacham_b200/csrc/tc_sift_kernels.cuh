@@ -74,22 +74,36 @@ struct SmemSift {
     uint8_t b[kBStages][tc::kBlockBytes];         // 128 rows of `second`, whole pre-tiled block (both augmentations)
     long long rowstate[kABlockRows][2];           // merged (best, second) composites of the resident rows, built at the end of a row block
     uint2 share1[kColParts][kABlockRows];         // D1: every column part's running (best, second) keys of the resident rows -- the other parts' bars
-    uint32_t tiles1[kColParts][kABlockRows];      // D1: their tile ids (t0 | t1 << 16), published at the end of a row block
+    uint2 tiles1[kColParts][kABlockRows];         // D1: their tile ids (t0 | t1 << 16) and their smallest passed-over score, published at the end of a row block
+    int32_t rowskip[kABlockRows];                 // smallest passed-over score of the resident rows over all parts (end of a row block)
     uint64_t b_full[kBStages], b_empty[kBStages], a_full, a_empty, acc_full[2], acc_empty[2];
     uint32_t tmem_slot;
     uint32_t red[2 * kEpiWarps + 8];
     unsigned long long base;
 };
 
-// The bar of a query from the running (best, second) keys of its four column parts: the second smallest of the eight keys, rounded
-// up to the next multiple of 256. A score can still enter the merged top two (or tie with its second and win on the index) only
-// if (score bits & ~0xFF) <= second & ~0xFF, i.e. iff score bits < bar. Any STALE copy of a part's keys gives a valid (higher) bar.
-__device__ __forceinline__ int32_t bar_of8(uint2 a, uint2 b, uint2 c, uint2 d) {
+// What a query still has to look at.
+//   (1) Only a score below its second best can enter its top two: bar <= second best (rounded up to the next multiple of 256, the
+//       key granularity, so that ties go through and are settled by the index).
+//   (2) The OUTPUT for a query is its best neighbour's index if best / second < ratio, else nothing. A score x >= ratio^2 * best
+//       (scores are squared distances / 2) can never be the best of a MATCH: as a new best it would have the old best as a second
+//       at ratio >= `ratio`; as a second it only decides match / no match, for which its VALUE is enough. So such scores are not
+//       inserted at all (r2s = ratio^2 plus a margin); the smallest of them is kept per query (`skip`, a running minimum -- it
+//       changes O(log n) times) and rerank_range folds it into the decision with the scorer's error bound, falling back to the
+//       exact scan in the rare case where the decision would hinge on a passed-over score's exact value. Insertions drop from
+//       every new best-or-second to the new bests of potential matches.
+__device__ __forceinline__ int32_t low_bar(int32_t best_key, float r2s) {
+    return (__float_as_int(__int_as_float(best_key & (int32_t)0xFFFFFF00) * r2s) + 255) & ~255;
+}
+__device__ __forceinline__ int32_t bar_of2(int32_t c0, int32_t c1, float r2s) { return min((c1 + 255) & ~255, low_bar(c0, r2s)); }
+// from the running (best, second) keys of the query's four column parts: the second smallest of the eight keys and the smallest
+// best. Any STALE copy of a part's keys gives a valid (higher) bar.
+__device__ __forceinline__ int32_t bar_of8(uint2 a, uint2 b, uint2 c, uint2 d, float r2s) {
     const int32_t a0 = (int32_t)a.x, b0 = (int32_t)b.x, c0 = (int32_t)c.x, d0 = (int32_t)d.x;
     const int32_t lo01 = min(a0, b0), hi01 = max(a0, b0), lo23 = min(c0, d0), hi23 = max(c0, d0);
     const int32_t x = min(min(hi01, hi23), max(lo01, lo23));                                     // second smallest of the four bests
     const int32_t y = min(min((int32_t)a.y, (int32_t)b.y), min((int32_t)c.y, (int32_t)d.y));     // smallest of the four seconds
-    return (min(x, y) + 255) & ~255;
+    return min((min(x, y) + 255) & ~255, low_bar(min(lo01, lo23), r2s));
 }
 
 __device__ __forceinline__ long long comp_of(uint32_t key, uint32_t base) {
@@ -115,9 +129,9 @@ __device__ __forceinline__ void insert(int32_t key, int32_t& c0, int32_t& c1) {
 }
 
 // 8 scores v[kOff .. kOff + 8) of one query (bit patterns of D as signed integers), index byte kIdx0 + position. c0 <= c1: the
-// tile-local candidates (keys); bar: scores >= bar are of no interest. Warp-uniform control flow.
+// query's running candidates (keys); bar: scores >= bar are not inserted; skip: the smallest score passed over. Warp-uniform control flow.
 template <int kIdx0, int kOff>
-__device__ __forceinline__ void scan8(const uint32_t (&v)[16], uint32_t mask, int32_t& c0, int32_t& c1, int32_t& bar) {
+__device__ __forceinline__ void scan8(const uint32_t (&v)[16], uint32_t mask, float r2s, int32_t& c0, int32_t& c1, int32_t& bar, int32_t& skip) {
     const int32_t x0 = (int32_t)v[kOff + 0], x1 = (int32_t)v[kOff + 1], x2 = (int32_t)v[kOff + 2], x3 = (int32_t)v[kOff + 3];
     const int32_t x4 = (int32_t)v[kOff + 4], x5 = (int32_t)v[kOff + 5], x6 = (int32_t)v[kOff + 6], x7 = (int32_t)v[kOff + 7];
     const int32_t mn = min(min(min(x0, x1), x2), min(min(min(x3, x4), x5), min(x6, x7)));      // four instructions (three 3-input minima)
@@ -128,13 +142,15 @@ __device__ __forceinline__ void scan8(const uint32_t (&v)[16], uint32_t mask, in
         insert(key_of<kIdx0 + 2>(v[kOff + 2], mask), c0, c1); insert(key_of<kIdx0 + 3>(v[kOff + 3], mask), c0, c1);
         insert(key_of<kIdx0 + 4>(v[kOff + 4], mask), c0, c1); insert(key_of<kIdx0 + 5>(v[kOff + 5], mask), c0, c1);
         insert(key_of<kIdx0 + 6>(v[kOff + 6], mask), c0, c1); insert(key_of<kIdx0 + 7>(v[kOff + 7], mask), c0, c1);
-        bar = min(bar, (c1 + 255) & ~255);
+        bar = min(bar, bar_of2(c0, c1, r2s));
+    } else {
+        skip = min(skip, mn);                             // all eight passed over (by every lane)
     }
 }
 template <int kIdx0>
-__device__ __forceinline__ void scan16(const uint32_t (&v)[16], uint32_t mask, int32_t& c0, int32_t& c1, int32_t& bar) {
-    scan8<kIdx0, 0>(v, mask, c0, c1, bar);
-    scan8<kIdx0 + 8, 8>(v, mask, c0, c1, bar);
+__device__ __forceinline__ void scan16(const uint32_t (&v)[16], uint32_t mask, float r2s, int32_t& c0, int32_t& c1, int32_t& bar, int32_t& skip) {
+    scan8<kIdx0, 0>(v, mask, r2s, c0, c1, bar, skip);
+    scan8<kIdx0 + 8, 8>(v, mask, r2s, c0, c1, bar, skip);
 }
 
 // sum over the 32 lanes of 16 values per lane at once: afterwards lanes 2r and 2r + 1 hold the total of value r in p[0]. Same offsets
@@ -155,14 +171,14 @@ __device__ __forceinline__ void multi_reduce16(float (&p)[16], int lane) {
 }
 
 // Exact re-rank + ratio test (FeatureMatcherFlann.cpp:21-27) of a strided range of queries: query q_first + k * step (k < n_iter,
-// q < q_end) has its two candidates in state[(s_first + k * step) * 2 ..]. Sixteen queries per warp pass: every lane accumulates
+// q < q_end) has its two candidates in state[(s_first + k * step) * 2 ..] and its smallest passed-over score in skip[..]. Sixteen queries per warp pass: every lane accumulates
 // its four dimensions of all sixteen (query, candidate) distances, one multi-value butterfly per candidate sums them, and lane
 // 2r (and 2r + 1) then runs the certainty logic of tcm::rerank_ratio_checked for query r -- same arithmetic, same bits, but the
 // scalar part once per sixteen queries instead of once per query, and twelve gathered rows in flight per warp instead of three
 // (one query at a time was measured at ~2,400 cycles per query, a fifth of the kernel). The only difference: the query's own norm
 // in the error bound is replaced by its image's maximum norm (still a bound). Not inlined: its registers must not leak into the
 // scan loop's allocation.
-__device__ __noinline__ void rerank_range(const long long* state, uint32_t s_first, uint32_t q_first, uint32_t step, uint32_t n_iter, uint32_t q_end,
+__device__ __noinline__ void rerank_range(const long long* state, const int32_t* skip, uint32_t s_first, uint32_t q_first, uint32_t step, uint32_t n_iter, uint32_t q_end,
                                           const float* __restrict__ Q, const float* __restrict__ T, uint32_t n_train, double ratio, int lane,
                                           bool exact_inputs, float own_max_norm, float other_max_norm, uint32_t* fallbacks, int32_t* dbg_idx, float* dbg_dist,
                                           uint32_t* out) {
@@ -205,23 +221,41 @@ __device__ __noinline__ void rerank_range(const long long* state, uint32_t s_fir
         const bool v0 = j0 < n_train, v1 = j1 < n_train;
         float d0 = v0 ? __fsqrt_rn(p0[0]) : kInf, d1 = v1 ? __fsqrt_rn(p1[0]) : kInf;
         if (d1 < d0 || (d1 == d0 && j1 < j0)) { const float t = d0; d0 = d1; d1 = t; const uint32_t u = j0; j0 = j1; j1 = u; }
+        // The decision (tcm::rerank_ratio_checked, extended by the passed-over scores of the pruned sweep). Every train row other than
+        // the two candidates is either (a) a row the candidates pushed out or kept out: its score was >= score(j1), so its squared
+        // distance is >= X = d1^2 - 4E; or (b) a row that was passed over: its score was >= S (the smallest such score of this query),
+        // so its distance is >= ds_lo, and the row that had score S is at most ds_hi away. With L a lower bound on the distance of
+        // every non-candidate and U an upper bound on the distance of SOME row other than j0:
+        //   j0 is the match for certain    if d0 < L and d0 / min(d1, L) < ratio
+        //   there is no match for certain  if d0 / min(d1, U) >= ratio and (L >= d0 or L / d0 >= ratio)   (second case: a non-candidate is the best)
+        //   otherwise                      exact scan over all train rows
+        const int32_t skey = valid ? skip[si] : kEmptyKeyTc;
+        const float S = __int_as_float(skey);
+        const bool has_skip = valid && S < 1.0e29f;       // (>= 1e29: only padding rows were passed over)
         uint32_t result = EACHAM_NONE;
         bool certain = true;
-        if (v0 && v1) {                                  // fewer than two neighbours: the reference is UB, rejected
-            float E = 0.5f * d1 * d1 * 3.0517578125e-5f;                                   // E_trunc
-            if (!exact_inputs) {
-                const float na = own_max_norm * 1.004f, nb = other_max_norm * 1.004f;
-                const float delta = 1.953125e-3f * (na + nb) * 1.01f;
-                E += 0.5f * delta * (2.f * d1 + delta) + 1.52587890625e-5f * 0.5f * (na * na + nb * nb);
+        if (v0 && (v1 || has_skip)) {                    // fewer than two neighbours: the reference is UB, rejected
+            float na = 0.f, nb = 0.f, delta = 0.f;
+            if (!exact_inputs) { na = own_max_norm * 1.004f; nb = other_max_norm * 1.004f; delta = 1.953125e-3f * (na + nb) * 1.01f; }
+            float L = kInf, U = kInf;
+            if (v1) {
+                float E = 0.5f * d1 * d1 * 3.0517578125e-5f;                               // E_trunc
+                if (!exact_inputs) E += 0.5f * delta * (2.f * d1 + delta) + 1.52587890625e-5f * 0.5f * (na * na + nb * nb);
+                const float X = d1 * d1 - 4.f * E * 1.001f;
+                L = X > 0.f ? sqrtf(X) * 0.999999f : 0.f;
             }
-            const float X = d1 * d1 - 4.f * E * 1.001f;
-            const bool lo_pass = (double)__fdiv_rn(d0, d1) < ratio;
+            if (has_skip) {
+                const float ds = sqrtf(2.f * fmaxf(S, 0.f));
+                const float Et = fabsf(S) * 3.0517578125e-5f * 1.01f;                      // S is the floor of a 16-mantissa-bit key
+                const float En = exact_inputs ? 0.f : (0.5f * delta * (2.f * ds + 3.f * delta) + 1.52587890625e-5f * 0.5f * (na * na + nb * nb)) * 1.01f;
+                L = fminf(L, sqrtf(2.f * fmaxf(S - En, 0.f)) * 0.999999f);
+                U = sqrtf(2.f * fmaxf(S + Et + En, 0.f)) * 1.000001f;
+            }
+            const float lo2 = fminf(d1, L);
+            const bool no_match = U < d1 ? (double)(d0 / U) >= ratio * 1.000001 : !((double)__fdiv_rn(d0, d1) < ratio);
             certain = false;
-            if (X > 0.f) {
-                const float sx = sqrtf(X) * 0.999999f;
-                if ((double)(d0 / sx * 1.000001f) < ratio) { certain = true; result = j0; }
-                else if (!lo_pass && (double)sx >= ratio * (double)d0 * 1.000001) certain = true;
-            }
+            if (d0 < L && (double)(d0 / lo2 * 1.000001f) < ratio) { certain = true; result = j0; }
+            else if (no_match && (L >= d0 || (double)L >= ratio * (double)d0 * 1.000001)) certain = true;
         }
         // the uncertain ones: exact scan over all train rows, one query at a time, the whole warp on each
         unsigned need = __ballot_sync(0xffffffffu, valid && !certain && (lane & 1) == 0);
@@ -249,12 +283,13 @@ __device__ __noinline__ void rerank_range(const long long* state, uint32_t s_fir
 // its tile ids in S.tiles1; returns the advanced MMA step counter. Not inlined: the loop gets its own register allocation (inlined into
 // the kernel it ran at the 96-register cap with spills inside the tile loop).
 __device__ __noinline__ uint32_t scan_block(SmemSift& S, uint32_t tmem, int q, int cp, int lane, int e, uint32_t blk0, uint32_t nh, uint32_t nbt, uint32_t N, uint32_t M,
-                                            uint32_t ab, bool both, uint2* colkeys, uint32_t* coltiles, uint32_t step_it) {
+                                            uint32_t ab, bool both, float r2s, uint2* colkeys, uint2* colts, uint32_t step_it) {
     uint32_t mask = 0xFFFFFF00u;
     asm volatile("" : "+r"(mask));                       // keep the mask in a register: key = (v & mask) | immediate is one LOP3
     // this part's running candidates of its two resident rows (keys: score bits | column within the part), and their tiles
     int32_t m0[2] = {kEmptyKeyTc, kEmptyKeyTc}, m1[2] = {kEmptyKeyTc, kEmptyKeyTc};
     uint32_t t0[2] = {0xFFFFu, 0xFFFFu}, t1[2] = {0xFFFFu, 0xFFFFu};
+    int32_t skip1[2] = {kEmptyKeyTc, kEmptyKeyTc};       // smallest score passed over (bar_of2 / bar_of8)
     const int r0 = q * 32 + lane, r1 = 128 + q * 32 + lane;
     const bool rv0 = blk0 * 128 + r0 < N, rv1 = nh == 2 && blk0 * 128 + r1 < N;
     S.share1[cp][r0] = make_uint2((uint32_t)kEmptyKeyTc, (uint32_t)kEmptyKeyTc);
@@ -265,11 +300,11 @@ __device__ __noinline__ uint32_t scan_block(SmemSift& S, uint32_t tmem, int q, i
         const uint32_t jrow = bt * 128 + q * 32 + lane;
         // this tile's rows of the second image: their four parts' keys and this part's block ids, requested ahead of D2 (L2 latency)
         uint4 ka = make_uint4(0u, 0u, 0u, 0u), kb = ka;
-        uint32_t tt = 0;
+        uint2 ts = make_uint2(0u, 0u);                   // this part's (row-block ids, smallest passed-over score) of the row
         if (both) {
             ka = reinterpret_cast<const uint4*>(colkeys)[2 * (size_t)jrow];
             kb = reinterpret_cast<const uint4*>(colkeys)[2 * (size_t)jrow + 1];
-            tt = coltiles[4 * (size_t)jrow + cp];
+            ts = colts[4 * (size_t)jrow + cp];
         }
         // ---------------- D1: each lane owns one row of each resident half; 32 columns per warp ----------------
         {
@@ -277,8 +312,8 @@ __device__ __noinline__ uint32_t scan_block(SmemSift& S, uint32_t tmem, int q, i
             // bars from all four parts' published keys, every fourth tile (unsynchronised: stale only means a higher bar); in between
             // the bar only follows this part's own insertions. Padding rows never take part.
             if ((bt & (kBarEvery - 1u)) == 1u) {
-                if (rv0) bar1[0] = min(bar1[0], bar_of8(S.share1[0][r0], S.share1[1][r0], S.share1[2][r0], S.share1[3][r0]));
-                if (rv1) bar1[1] = min(bar1[1], bar_of8(S.share1[0][r1], S.share1[1][r1], S.share1[2][r1], S.share1[3][r1]));
+                if (rv0) bar1[0] = min(bar1[0], bar_of8(S.share1[0][r0], S.share1[1][r0], S.share1[2][r0], S.share1[3][r0], r2s));
+                if (rv1) bar1[1] = min(bar1[1], bar_of8(S.share1[0][r1], S.share1[1][r1], S.share1[2][r1], S.share1[3][r1], r2s));
             }
             const int32_t o00 = m0[0], o10 = m1[0], o01 = m0[1], o11 = m1[1];
             if (lane == 0 && (e == 0 || e == 5)) SIFT_TRACE(e == 5, step_it >> 1, 0);
@@ -292,16 +327,16 @@ __device__ __noinline__ uint32_t scan_block(SmemSift& S, uint32_t tmem, int q, i
                 tc::tmem_ld16(taddr, v);
                 tc::tmem_ld_wait();
                 tc::tmem_ld16(taddr + 16, w);
-                scan16<0>(v, mask, m0[0], m1[0], bar1[0]);
+                scan16<0>(v, mask, r2s, m0[0], m1[0], bar1[0], skip1[0]);
                 tc::tmem_ld_wait();
                 if (nh == 2) tc::tmem_ld16(taddr + 128, v);
-                scan16<16>(w, mask, m0[0], m1[0], bar1[0]);
+                scan16<16>(w, mask, r2s, m0[0], m1[0], bar1[0], skip1[0]);
                 if (nh == 2) {
                     tc::tmem_ld_wait();
                     tc::tmem_ld16(taddr + 144, w);
-                    scan16<0>(v, mask, m0[1], m1[1], bar1[1]);
+                    scan16<0>(v, mask, r2s, m0[1], m1[1], bar1[1], skip1[1]);
                     tc::tmem_ld_wait();
-                    scan16<16>(w, mask, m0[1], m1[1], bar1[1]);
+                    scan16<16>(w, mask, r2s, m0[1], m1[1], bar1[1], skip1[1]);
                 }
             }
             tc::tc_fence_before();
@@ -323,8 +358,8 @@ __device__ __noinline__ uint32_t scan_block(SmemSift& S, uint32_t tmem, int q, i
             const uint32_t reg = step_it & 1;
             const uint32_t ncols = nh * 128;
             const uint2 own = cp == 0 ? make_uint2(ka.x, ka.y) : cp == 1 ? make_uint2(ka.z, ka.w) : cp == 2 ? make_uint2(kb.x, kb.y) : make_uint2(kb.z, kb.w);
-            int32_t c0 = (int32_t)own.x, c1 = (int32_t)own.y;
-            int32_t bar = jrow < M ? bar_of8(make_uint2(ka.x, ka.y), make_uint2(ka.z, ka.w), make_uint2(kb.x, kb.y), make_uint2(kb.z, kb.w)) : INT32_MIN;
+            int32_t c0 = (int32_t)own.x, c1 = (int32_t)own.y, skip = (int32_t)ts.y;
+            int32_t bar = jrow < M ? bar_of8(make_uint2(ka.x, ka.y), make_uint2(ka.z, ka.w), make_uint2(kb.x, kb.y), make_uint2(kb.z, kb.w), r2s) : INT32_MIN;
             tc::mbar_wait(&S.acc_full[reg], (step_it >> 1) & 1);
             tc::tc_fence_after();
             if (lane == 0 && (e == 0 || e == 5)) SIFT_TRACE(e == 5, step_it >> 1, 4);
@@ -334,32 +369,32 @@ __device__ __noinline__ uint32_t scan_block(SmemSift& S, uint32_t tmem, int q, i
                 tc::tmem_ld16(taddr, v);
                 tc::tmem_ld_wait();
                 tc::tmem_ld16(taddr + 16, w);
-                scan16<0>(v, mask, c0, c1, bar);
+                scan16<0>(v, mask, r2s, c0, c1, bar, skip);
                 tc::tmem_ld_wait();
                 tc::tmem_ld16(taddr + 32, v);
-                scan16<16>(w, mask, c0, c1, bar);
+                scan16<16>(w, mask, r2s, c0, c1, bar, skip);
                 tc::tmem_ld_wait();
                 tc::tmem_ld16(taddr + 48, w);
-                scan16<32>(v, mask, c0, c1, bar);
+                scan16<32>(v, mask, r2s, c0, c1, bar, skip);
                 tc::tmem_ld_wait();
-                scan16<48>(w, mask, c0, c1, bar);
+                scan16<48>(w, mask, r2s, c0, c1, bar, skip);
             }
             tc::tc_fence_before();
             __syncwarp();
             if (lane == 0) tc::mbar_arrive(&S.acc_empty[reg]);
             if (lane == 0 && (e == 0 || e == 5)) SIFT_TRACE(e == 5, step_it >> 1, 5);
             ++step_it;
-            if (c0 != (int32_t)own.x || c1 != (int32_t)own.y) {
-                uint32_t u0 = tt & 0xFFFFu, u1 = tt >> 16;
+            if (c0 != (int32_t)own.x || c1 != (int32_t)own.y || skip != (int32_t)ts.y) {      // all three are running minima: they change O(log n) times
+                uint32_t u0 = ts.x & 0xFFFFu, u1 = ts.x >> 16;
                 track(c0, c1, (int32_t)own.x, (int32_t)own.y, ab, u0, u1);
                 colkeys[4 * (size_t)jrow + cp] = make_uint2((uint32_t)c0, (uint32_t)c1);
-                coltiles[4 * (size_t)jrow + cp] = u0 | (u1 << 16);
+                colts[4 * (size_t)jrow + cp] = make_uint2(u0 | (u1 << 16), (uint32_t)skip);
             }
             if (lane == 0 && (e == 0 || e == 5)) SIFT_TRACE(e == 5, (step_it - 1) >> 1, 6);
         }
     }
-    S.tiles1[cp][r0] = t0[0] | (t1[0] << 16);
-    S.tiles1[cp][r1] = t0[1] | (t1[1] << 16);
+    S.tiles1[cp][r0] = make_uint2(t0[0] | (t1[0] << 16), (uint32_t)skip1[0]);
+    S.tiles1[cp][r1] = make_uint2(t0[1] | (t1[1] << 16), (uint32_t)skip1[1]);
     return step_it;
 }
 
@@ -504,9 +539,14 @@ __global__ void __launch_bounds__(kThreads, 1) sift_tc_match_pairs_kernel(const 
         const int et = e * 32 + lane;
         uint8_t* my_scratch = p.scratch + (size_t)blockIdx.x * tcm::tc_scratch_bytes_per_cta(p.rows_cap, p.cols_cap);
         uint2* colkeys = reinterpret_cast<uint2*>(my_scratch);                                      // [cols_cap][4 parts]: running (best, second) keys
-        uint32_t* coltiles = reinterpret_cast<uint32_t*>(my_scratch + (size_t)p.cols_cap * 32);     // [cols_cap][4 parts]: their row-block ids
-        long long* colstate = reinterpret_cast<long long*>(my_scratch + (size_t)p.cols_cap * 48);   // [cols_cap][2]: merged composites (end of pair)
-        uint32_t* m12 = reinterpret_cast<uint32_t*>(my_scratch + (size_t)p.cols_cap * 64);          // [rows_cap]
+        uint2* colts = reinterpret_cast<uint2*>(my_scratch + (size_t)p.cols_cap * 32);              // [cols_cap][4 parts]: (row-block ids, smallest passed-over score)
+        long long* colstate = reinterpret_cast<long long*>(my_scratch + (size_t)p.cols_cap * 64);   // [cols_cap][2]: merged composites (end of pair)
+        int32_t* colskip = reinterpret_cast<int32_t*>(my_scratch + (size_t)p.cols_cap * 80);        // [cols_cap]: merged smallest passed-over score
+        uint32_t* m12 = reinterpret_cast<uint32_t*>(my_scratch + (size_t)p.cols_cap * 96);          // [rows_cap]
+        // scores >= r2s * best are passed over (see low_bar). The margin covers the scorer's error, so that a passed-over score is
+        // practically never the best of a match (that case is still handled: exact scan). The debug view wants the true second
+        // neighbour, so it switches the rule off.
+        const float r2s = (p.dbg_idx12 != nullptr || p.dbg_idx21 != nullptr) ? 3.0e38f : (float)(p.ratio * p.ratio) * 1.0625f;
         uint32_t* m21 = m12 + p.rows_cap;                                                           // [cols_cap]
         uint32_t step_it = 0;
         for (uint32_t wk = blockIdx.x; wk < p.n_pairs; wk += gridDim.x) {
@@ -531,27 +571,32 @@ __global__ void __launch_bounds__(kThreads, 1) sift_tc_match_pairs_kernel(const 
                     const uint4 ek = make_uint4((uint32_t)kEmptyKeyTc, (uint32_t)kEmptyKeyTc, (uint32_t)kEmptyKeyTc, (uint32_t)kEmptyKeyTc);
                     reinterpret_cast<uint4*>(colkeys)[2 * (size_t)j] = ek;
                     reinterpret_cast<uint4*>(colkeys)[2 * (size_t)j + 1] = ek;
-                    reinterpret_cast<uint4*>(coltiles)[j] = make_uint4(0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu);
+                    const uint4 et4 = make_uint4(0xFFFFFFFFu, (uint32_t)kEmptyKeyTc, 0xFFFFFFFFu, (uint32_t)kEmptyKeyTc);
+                    reinterpret_cast<uint4*>(colts)[2 * (size_t)j] = et4;
+                    reinterpret_cast<uint4*>(colts)[2 * (size_t)j + 1] = et4;
                 }
 
             for (uint32_t ab = p.single_dir ? pi : 0u, ab1 = p.single_dir ? pi + 1 : (na128 + 1) / 2; ab < ab1; ++ab) {
                 const uint32_t blk0 = p.single_dir ? pi : ab * 2;
                 const uint32_t nh = p.single_dir ? 1u : min(2u, na128 - ab * 2);
-                step_it = scan_block(S, tmem, q, cp, lane, e, blk0, nh, nbt, N, M, ab, both, colkeys, coltiles, step_it);
+                step_it = scan_block(S, tmem, q, cp, lane, e, blk0, nh, nbt, N, M, ab, both, r2s, colkeys, colts, step_it);
                 // ---- rows of this block are complete: merge the four parts, re-rank exactly, ratio test ----
                 epi_bar();
                 if (et < kABlockRows) {
                     long long g0 = kEmptyComp, g1 = kEmptyComp;
+                    int32_t sk = kEmptyKeyTc;
 #pragma unroll
                     for (int c = 0; c < kColParts; ++c) {
                         const uint2 k = S.share1[c][et];
-                        const uint32_t tl = S.tiles1[c][et];
-                        tcm::comp_merge(comp_of(k.x, (tl & 0xFFFFu) * 128 + c * 32), comp_of(k.y, (tl >> 16) * 128 + c * 32), g0, g1);
+                        const uint2 tl = S.tiles1[c][et];
+                        tcm::comp_merge(comp_of(k.x, (tl.x & 0xFFFFu) * 128 + c * 32), comp_of(k.y, (tl.x >> 16) * 128 + c * 32), g0, g1);
+                        sk = min(sk, (int32_t)tl.y);
                     }
                     S.rowstate[et][0] = g0; S.rowstate[et][1] = g1;
+                    S.rowskip[et] = sk;
                 }
                 epi_bar();
-                rerank_range(&S.rowstate[0][0], e * (kABlockRows / kEpiWarps), blk0 * 128 + e * (kABlockRows / kEpiWarps), 1, kABlockRows / kEpiWarps,
+                rerank_range(&S.rowstate[0][0], S.rowskip, e * (kABlockRows / kEpiWarps), blk0 * 128 + e * (kABlockRows / kEpiWarps), 1, kABlockRows / kEpiWarps,
                              min(N, (blk0 + nh) * 128), Af, Bf, M, p.ratio, lane, both_exact, __uint_as_float(A.max_norm_bits), __uint_as_float(B.max_norm_bits), p.exact_fallbacks,
                              p.dbg_idx12, p.dbg_dist12, p.single_dir ? p.single_out : m12);
             }
@@ -562,17 +607,18 @@ __global__ void __launch_bounds__(kThreads, 1) sift_tc_match_pairs_kernel(const 
             epi_bar();
             for (uint32_t j = et; j < M; j += kEpiThreads) {
                 const uint4 ka = reinterpret_cast<const uint4*>(colkeys)[2 * (size_t)j], kb = reinterpret_cast<const uint4*>(colkeys)[2 * (size_t)j + 1];
-                const uint4 tl = reinterpret_cast<const uint4*>(coltiles)[j];
+                const uint4 ta = reinterpret_cast<const uint4*>(colts)[2 * (size_t)j], tb = reinterpret_cast<const uint4*>(colts)[2 * (size_t)j + 1];
                 long long g0 = kEmptyComp, g1 = kEmptyComp;
-                tcm::comp_merge(comp_of(ka.x, (tl.x & 0xFFFFu) * 256), comp_of(ka.y, (tl.x >> 16) * 256), g0, g1);
-                tcm::comp_merge(comp_of(ka.z, (tl.y & 0xFFFFu) * 256 + 64), comp_of(ka.w, (tl.y >> 16) * 256 + 64), g0, g1);
-                tcm::comp_merge(comp_of(kb.x, (tl.z & 0xFFFFu) * 256 + 128), comp_of(kb.y, (tl.z >> 16) * 256 + 128), g0, g1);
-                tcm::comp_merge(comp_of(kb.z, (tl.w & 0xFFFFu) * 256 + 192), comp_of(kb.w, (tl.w >> 16) * 256 + 192), g0, g1);
+                tcm::comp_merge(comp_of(ka.x, (ta.x & 0xFFFFu) * 256), comp_of(ka.y, (ta.x >> 16) * 256), g0, g1);
+                tcm::comp_merge(comp_of(ka.z, (ta.z & 0xFFFFu) * 256 + 64), comp_of(ka.w, (ta.z >> 16) * 256 + 64), g0, g1);
+                tcm::comp_merge(comp_of(kb.x, (tb.x & 0xFFFFu) * 256 + 128), comp_of(kb.y, (tb.x >> 16) * 256 + 128), g0, g1);
+                tcm::comp_merge(comp_of(kb.z, (tb.z & 0xFFFFu) * 256 + 192), comp_of(kb.w, (tb.z >> 16) * 256 + 192), g0, g1);
                 colstate[2 * (size_t)j] = g0; colstate[2 * (size_t)j + 1] = g1;
+                colskip[j] = min(min((int32_t)ta.y, (int32_t)ta.w), min((int32_t)tb.y, (int32_t)tb.w));
             }
             __threadfence_block();
             epi_bar();
-            rerank_range(colstate, e, e, kEpiWarps, (M + kEpiWarps - 1 - e) / kEpiWarps, M, Bf, Af, N, p.ratio, lane, both_exact, __uint_as_float(B.max_norm_bits), __uint_as_float(A.max_norm_bits),
+            rerank_range(colstate, colskip, e, e, kEpiWarps, (M + kEpiWarps - 1 - e) / kEpiWarps, M, Bf, Af, N, p.ratio, lane, both_exact, __uint_as_float(B.max_norm_bits), __uint_as_float(A.max_norm_bits),
                          p.exact_fallbacks, p.dbg_idx21, p.dbg_dist21, m21);
             __threadfence_block();
             epi_bar();
