@@ -29,7 +29,8 @@
 // Keys, composites and tie-breaking (lower index wins) are those of the round-1 kernel, so the candidates differ from it only where
 // D1 and D2 round differently (never for bf16-exact, e.g. integer-valued, inputs), and the match sets are exact either way
 // (tcm::rerank_ratio_checked's bound; the query's own norm is replaced by its image's maximum norm, still a bound).
-// Measured (200 images x 8192, 19,900 pairs): 29.1k pairs/s against 22.2k; tensor pipe 55 %, ALU 57 %.
+//   * ratio-aware pruning (low_bar / `skip`): scores that could only ever be the second of a non-match are not inserted at all.
+// Measured (500 images x 8192, 124,750 pairs): 32.8k pairs/s against 22.4k; tensor pipe 69 %, ALU 51 %.
 #pragma once
 #include <cstdint>
 #include <cstdio>
