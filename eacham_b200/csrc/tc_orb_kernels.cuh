@@ -294,6 +294,7 @@ __global__ void __launch_bounds__(kThreads, 1) orb_tc_match_pairs_kernel(const P
         uint32_t* m12 = reinterpret_cast<uint32_t*>(my_scratch + (size_t)p.cols_cap * 32);     // [rows_cap]
         uint32_t* m21 = m12 + p.rows_cap;                                                      // [cols_cap]
         uint2* xp = S.u.xpose[e];
+        const uint32_t rbar = (uint32_t)__half_as_ushort(__float2half_rn((float)p.ratio * 1.0625f)) * 0x10001u;      // packed f16: ratio plus a margin (row bars)
         uint32_t acc_it = 0;
         for (uint32_t k = 0;; ++k) {
             const uint32_t rs = k % kRing;
@@ -323,6 +324,7 @@ __global__ void __launch_bounds__(kThreads, 1) orb_tc_match_pairs_kernel(const P
                 const uint32_t blk0 = p.single_dir ? pi : ab * 2;                     // first 128-row block of this work unit
                     const uint32_t nh = p.single_dir ? 1u : min(2u, na128 - ab * 2); (void)blk0;
                 uint32_t m0[2] = {kSentX2, kSentX2}, m1[2] = {kSentX2, kSentX2};       // packed (even | odd columns) top-2 per row half
+                uint32_t bar[2] = {kSentX2, kSentX2}, skip[2] = {kSentX2, kSentX2};   // scores >= bar are not merged; skip = the smallest of those
                 uint32_t t0[2] = {0u, 0u};                                             // packed f16: tile where m0 last decreased
                 uint32_t btx2 = 0u;                                                    // packed f16 (bt | bt)
                 const uint32_t abx2 = (uint32_t)__half_as_ushort(__uint2half_rn(ab)) * 0x10001u;          // packed f16 (ab | ab)
@@ -361,25 +363,49 @@ __global__ void __launch_bounds__(kThreads, 1) orb_tc_match_pairs_kernel(const P
                     }
                     __syncwarp();
                     // ---- rows (independent of the transpose: fills the shared-memory latency) ----
-                    const uint32_t o0 = m0[0], o1 = m0[1];
+                    // Pruned: what matters for a row is its best (with its tile) and whether anything else comes within 1 / ratio of
+                    // it. A score >= ratio * best (x 1.0625) can never be the best of a match -- the old best would be its second at
+                    // a ratio >= `ratio` -- so it is not merged; only the running minimum of such scores is kept (`skip`), and the
+                    // finalisation takes second = min(second, skip). Both are exact integers (D = hamming / 2), so nothing changes
+                    // in the result. One packed min tree + one compare per half; the merge runs only if some lane has a score
+                    // under its bar.
                     if (!(EACHAM_EXP & 1)) {
-                        uint32_t lo, hi;
-                        reduce16<kFmaSort>(v0, lo, hi);
-                        merge2(m0[0], m1[0], lo, hi, m0[0], m1[0]);
-                        reduce16<kFmaSort>(v1, lo, hi);
-                        merge2(m0[1], m1[1], lo, hi, m0[1], m1[1]);
+                        uint32_t mn0 = min3u2(min3u2(v0[0], v0[1], v0[2]), min3u2(v0[3], v0[4], v0[5]), min3u2(v0[6], v0[7], v0[8]));
+                        mn0 = min3u2(mn0, min3u2(v0[9], v0[10], v0[11]), min3u2(v0[12], v0[13], v0[14]));
+                        mn0 = minu2(mn0, v0[15]);
+                        uint32_t mn1 = min3u2(min3u2(v1[0], v1[1], v1[2]), min3u2(v1[3], v1[4], v1[5]), min3u2(v1[6], v1[7], v1[8]));
+                        mn1 = min3u2(mn1, min3u2(v1[9], v1[10], v1[11]), min3u2(v1[12], v1[13], v1[14]));
+                        mn1 = minu2(mn1, v1[15]);
+                        const bool hit = minu2(mn0, bar[0]) != bar[0] || minu2(mn1, bar[1]) != bar[1];     // some 16-bit lane below its bar
+                        if (__any_sync(0xffffffffu, hit)) {
+                            const uint32_t o0 = m0[0], o1 = m0[1];
+                            uint32_t lo, hi;
+                            reduce16<kFmaSort>(v0, lo, hi);
+                            merge2(m0[0], m1[0], lo, hi, m0[0], m1[0]);
+                            reduce16<kFmaSort>(v1, lo, hi);
+                            merge2(m0[1], m1[1], lo, hi, m0[1], m1[1]);
+                            // tile of the running best: t0 = max(t0, changed ? bt : 0), per 16-bit lane, in f16 arithmetic
+                            const uint32_t k1024 = 0x64006400u;
+                            uint32_t d, c;
+                            asm("sub.f16x2 %0, %1, %2;" : "=r"(d) : "r"(o0), "r"(m0[0]));
+                            asm("mul.f16x2 %0, %1, %2;" : "=r"(c) : "r"(d), "r"(k1024));      // 0 or >= 512 (inf is fine)
+                            asm("min.f16x2 %0, %1, %2;" : "=r"(c) : "r"(c), "r"(btx2));
+                            asm("max.f16x2 %0, %1, %2;" : "=r"(t0[0]) : "r"(t0[0]), "r"(c));
+                            asm("sub.f16x2 %0, %1, %2;" : "=r"(d) : "r"(o1), "r"(m0[1]));
+                            asm("mul.f16x2 %0, %1, %2;" : "=r"(c) : "r"(d), "r"(k1024));
+                            asm("min.f16x2 %0, %1, %2;" : "=r"(c) : "r"(c), "r"(btx2));
+                            asm("max.f16x2 %0, %1, %2;" : "=r"(t0[1]) : "r"(t0[1]), "r"(c));
+                            uint32_t tl;
+                            asm("mul.f16x2 %0, %1, %2;" : "=r"(tl) : "r"(m0[0]), "r"(rbar));
+                            bar[0] = minu2(m1[0], tl);
+                            asm("mul.f16x2 %0, %1, %2;" : "=r"(tl) : "r"(m0[1]), "r"(rbar));
+                            bar[1] = minu2(m1[1], tl);
+                        } else {
+                            skip[0] = minu2(skip[0], mn0);
+                            skip[1] = minu2(skip[1], mn1);
+                        }
                     }
-                    {   // tile of the running best: t0 = max(t0, changed ? bt : 0), per 16-bit lane, in f16 arithmetic
-                        const uint32_t k1024 = 0x64006400u;
-                        uint32_t d, c;
-                        asm("sub.f16x2 %0, %1, %2;" : "=r"(d) : "r"(o0), "r"(m0[0]));
-                        asm("mul.f16x2 %0, %1, %2;" : "=r"(c) : "r"(d), "r"(k1024));      // 0 or >= 512 (inf is fine)
-                        asm("min.f16x2 %0, %1, %2;" : "=r"(c) : "r"(c), "r"(btx2));
-                        asm("max.f16x2 %0, %1, %2;" : "=r"(t0[0]) : "r"(t0[0]), "r"(c));
-                        asm("sub.f16x2 %0, %1, %2;" : "=r"(d) : "r"(o1), "r"(m0[1]));
-                        asm("mul.f16x2 %0, %1, %2;" : "=r"(c) : "r"(d), "r"(k1024));
-                        asm("min.f16x2 %0, %1, %2;" : "=r"(c) : "r"(c), "r"(btx2));
-                        asm("max.f16x2 %0, %1, %2;" : "=r"(t0[1]) : "r"(t0[1]), "r"(c));
+                    {
                         const uint32_t one = 0x3C003C00u;
                         asm("add.f16x2 %0, %1, %2;" : "=r"(btx2) : "r"(btx2), "r"(one));
                     }
@@ -422,7 +448,7 @@ __global__ void __launch_bounds__(kThreads, 1) orb_tc_match_pairs_kernel(const P
                 quad_bar(q);
                 uint4* rm = reinterpret_cast<uint4*>(S.u.xpose[q]);
 #pragma unroll
-                for (int h = 0; h < 2; ++h) rm[(cp * 2 + h) * 32 + lane] = make_uint4(m0[h], m1[h], t0[h], 0u);
+                for (int h = 0; h < 2; ++h) rm[(cp * 2 + h) * 32 + lane] = make_uint4(m0[h], m1[h], t0[h], skip[h]);
                 quad_bar(q);
                 {
                     // two threads per row: both merge the parts, each checks 8 of the 16 candidate columns
@@ -437,7 +463,7 @@ __global__ void __launch_bounds__(kThreads, 1) orb_tc_match_pairs_kernel(const P
                             const uint32_t v = (o.x >> (16 * par)) & 0xFFFFu, w = (o.y >> (16 * par)) & 0xFFFFu;
                             if (v < best) { second = min(second, best); best = v; wt = (o.z >> (16 * par)) & 0xFFFFu; wid = c * 2 + par; }
                             else second = min(second, v);
-                            second = min(second, w);
+                            second = min(second, min(w, (o.w >> (16 * par)) & 0xFFFFu));      // second best merged, or the smallest score passed over
                         }
                     }
                     uint32_t found = EACHAM_NONE, ham0 = 0;
