@@ -10,6 +10,7 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
+#include <exception>
 #include <mutex>
 #include <new>
 #include <string>
@@ -356,13 +357,17 @@ int eacham_gpu_set_descriptors_batch(eacham_gpu_handle* h, uint32_t first_id, ui
     const unsigned workers = (unsigned)std::min<size_t>(std::min(hw, 8u), std::max<size_t>(1, total >> 22));      // one per 4 MiB, at most 8
     if (workers <= 1) copy_range(0, n);
     else {
-        // contiguous ranges of about equal bytes
+        // contiguous ranges of about equal bytes; a range whose thread cannot be started is copied by the caller
         std::vector<std::thread> pool;
         uint32_t lo = 0;
         size_t acc = 0, share = (total + workers - 1) / workers;
         for (uint32_t i = 0; i < n; ++i) {
             acc += align_up((size_t)rows[i] * rb, kAlign);
-            if (acc >= share || i + 1 == n) { pool.emplace_back(copy_range, lo, i + 1); lo = i + 1; acc = 0; }
+            if (acc >= share || i + 1 == n) {
+                try { pool.emplace_back(copy_range, lo, i + 1); }
+                catch (const std::exception&) { copy_range(lo, i + 1); }
+                lo = i + 1; acc = 0;
+            }
         }
         for (std::thread& t : pool) t.join();
     }

@@ -7,7 +7,7 @@
  *   eacham_gpu_match        <- FeatureMatcherFlann::Match      modules/base/features/FeatureMatcherFlann.cpp:14-30
  *                              (IFeatureMatcher<T>::Match       modules/base/features/IFeatureMatcher.h:18-19)
  *   eacham_gpu_match_pairs  <- the pair loop + cross-check      apps/sfm/main.cpp:84-147
- *   eacham_gpu_set_descriptors / eacham_gpu_commit
+ *   eacham_gpu_set_descriptors(_batch) / eacham_gpu_commit
  *                           <- Node::GetDescriptors() feeding Match   modules/sfm/data/Node.h:136-139, apps/sfm/main.cpp:107-108
  *   eacham_match_t          <- one entry of match_t              modules/sfm/data/Types.h:34
  *
