@@ -116,3 +116,48 @@ def test_batched_path_distances_against_opencv(integer):
         if integer:
             assert np.array_equal(pm.matches.reshape(-1, 2), np.asarray(want["matches"]).reshape(-1, 2))
             assert m.timing()["exact_fallbacks"] <= 4
+
+
+def test_passed_over_scores_decide_correctly():
+    """The pruned sweep (tc_sift_kernels.cuh: low_bar / skip) does not insert scores >= ~0.68 x the running best; only their minimum is
+    kept and folded into the decision. Scenarios with EXACT integer distances (query = 256 e_s; train rows = 256 e_s + d e_(64+s), so the
+    distance is d; every other row is >= 320 away) placed so that the interesting rows arrive AFTER a bar exists (later tiles):
+      a passed-over row is the true best (no match), the true second (match and no match), exactly at the ratio (no match: 0.8f >= 0.8
+      as a double), and a chain of passed-over / inserted bests. Both engines that share the rule must equal OpenCV."""
+    import eacham_b200
+    scen = [
+        # (distances in arrival order: (row index, d)), expected: index of the matched row or None
+        ([(3, 100), (500, 85)], None),                      # 85 passed over, is the true best: 85 / 100 -> no match
+        ([(4, 100), (501, 79)], 501),                       # 79 is inserted: 79 / 100 -> match
+        ([(5, 50), (502, 62), (630, 63)], None),            # second passed over: 50 / 62 = 0.806 -> no match
+        ([(6, 50), (503, 63), (631, 64)], 6),               # second passed over: 50 / 63 = 0.794 -> match
+        ([(7, 40), (504, 50)], None),                       # exactly 0.8 -> no match
+        ([(8, 100), (505, 90), (632, 81), (700, 73)], None),  # 90 passed, 81 inserted, 73 passed: best 73, second 81 -> no match
+        ([(9, 100), (506, 90), (633, 60)], 633),            # 90 passed, 60 inserted: 60 / 90 -> match
+        ([(10, 120), (300, 200), (507, 110), (634, 109)], None),   # two passed-over bests in a row: 109 / 110 -> no match
+    ]
+    n_train = 768
+    q = np.zeros((len(scen), 128), np.float32)
+    t = np.zeros((n_train, 128), np.float32)
+    used = set()
+    for s, (rows, _) in enumerate(scen):
+        q[s, s] = 256
+        for j, d in rows:
+            assert j not in used
+            used.add(j)
+            t[j, s] = 256; t[j, 64 + s] = d
+    rng = np.random.default_rng(9)
+    for j in range(n_train):
+        if j not in used:                                   # fillers: >= 320 from every query, integer-valued
+            t[j, 32 + (j % 16)] = 200
+            t[j, 100 + rng.integers(0, 20)] = rng.integers(1, 60)
+    want = _ref_pair(q, t, min_dir=0, min_mutual=0)
+    for engine in ("tensor", "tensor_v1"):
+        with eacham_b200.FeatureMatcherGpu(0.8, sift_engine=engine, min_dir=0, min_mutual=0, cross_check=False) as m:
+            m.Upload([q, t])
+            got = m.Match(q, t)                             # per-call route: same kernel, single-direction mode
+            for s, (_, exp) in enumerate(scen):
+                assert got.get(s) == exp, (engine, s, got.get(s), exp)
+            pm = m.MatchPairs([(0, 1)], emit_all=True)[0]
+            assert (pm.n12, pm.n21) == (want["n12"], want["n21"]), engine
+        assert sum(e is not None for _, e in scen) == want["n12"]
