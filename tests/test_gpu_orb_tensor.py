@@ -58,3 +58,50 @@ def test_engines_agree_on_an_exhaustive_set(tmatcher):
                               b2[int(r2[k]["offset"]): int(r2[k]["offset"] + r2[k]["count"])])
     assert int(r1["count"].sum()) > 0
     matcher.close()
+
+
+def test_passed_over_scores_decide_correctly_orb():
+    """The pruned rows path of the default ORB engine (tc_orb_kernels.cuh) does not merge scores >= 0.85 x the running best; only their
+    minimum is kept and folded into the second best. Scenarios with chosen Hamming distances (query s = a 32-bit signature; its train rows
+    = the signature + d more bits; everything else is >= 64 bits away), the interesting rows arriving in later tiles: a passed-over row is
+    the true best, the true second (match and no match), exactly at the ratio, alternating chains. Batched and per-call routes, against the
+    C oracle and the XOR+POPC engine."""
+    import eacham_b200
+    scen = [
+        ([(3, 50), (500, 45)], None),
+        ([(4, 50), (501, 39)], 501),
+        ([(5, 30), (502, 37), (630, 38)], None),
+        ([(6, 30), (503, 38), (631, 39)], 6),
+        ([(7, 40), (504, 50)], None),
+        ([(8, 60), (505, 54), (632, 50), (700, 44)], None),
+        ([(9, 60), (506, 54), (633, 40)], 633),
+    ]
+    n_train = 768
+
+    def bits_to_bytes(b):
+        return np.packbits(b.astype(np.uint8), axis=-1, bitorder="little")
+
+    qb = np.zeros((len(scen), 256), np.uint8)
+    tb = np.zeros((n_train, 256), np.uint8)
+    used = set()
+    for s, (rows, _) in enumerate(scen):
+        qb[s, s * 16:s * 16 + 32 if s * 16 + 32 <= 128 else 128] = 1
+        for j, d in rows:
+            assert j not in used
+            used.add(j)
+            tb[j] = qb[s]
+            tb[j, 128:128 + d] = 1
+    rng = np.random.default_rng(13)
+    for j in range(n_train):
+        if j not in used:
+            tb[j] = rng.integers(0, 2, 256)
+    q, t = bits_to_bytes(qb), bits_to_bytes(tb)
+    want = O.c_match(q, t)
+    assert all(want.get(s) == e for s, (_, e) in enumerate(scen)), want
+    for engine in ("tensor", "popc"):
+        with eacham_b200.FeatureMatcherGpu(0.8, orb_engine=engine, min_dir=0, min_mutual=0, cross_check=False) as m:
+            assert m.Match(q, t) == want, engine
+            m.Upload([q, t])
+            pm = m.MatchPairs([(0, 1)], emit_all=True)[0]
+            ref = O.c_match_pair(q, t, min_dir=0, min_mutual=0)
+            assert (pm.n12, pm.n21, pm.n_mutual) == (ref["n12"], ref["n21"], ref["n_mutual"]), engine
