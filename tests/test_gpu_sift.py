@@ -181,3 +181,21 @@ def test_sift_engines_agree_on_large_images():
         assert x.n12 > 100 and x.n21 > 100
         assert (x.n12, x.n21, x.n_mutual) == (y.n12, y.n21, y.n_mutual) == (z.n12, z.n21, z.n_mutual)
         assert np.array_equal(x.matches, y.matches) and np.array_equal(x.matches, z.matches)
+
+
+@pytest.mark.parametrize("ratio", [0.6, 0.95])
+def test_sift_other_ratios(ratio):
+    """The pruning bar of the default SIFT engine is derived from the ratio (ratio^2 x best): other thresholds than 0.8, against OpenCV,
+    batched and per-call."""
+    import eacham_b200
+    from eacham_b200 import synth
+    a, b = synth.sift_image_set(2, 1400, seed=31, pool=2200, share=0.5)
+    b = np.ascontiguousarray(b[:1100])
+    want = _ref_pair(a, b, ratio=ratio, min_dir=0, min_mutual=0)
+    with eacham_b200.FeatureMatcherGpu(ratio, ratio=ratio, min_dir=0, min_mutual=0) as m:
+        m.Upload([a, b])
+        pm = m.MatchPairs([(0, 1)], emit_all=True)[0]
+        assert (pm.n12, pm.n21, pm.n_mutual) == (want["n12"], want["n21"], want["n_mutual"])
+        assert np.array_equal(pm.matches, np.asarray(want["matches"]).reshape(-1, 2))
+        one = m.Match(a, b)
+        assert len(one) == want["n12"]
