@@ -247,7 +247,7 @@ __device__ __noinline__ void rerank_range(const long long* state, const int32_t*
             }
             if (has_skip) {
                 const float ds = sqrtf(2.f * fmaxf(S, 0.f));
-                const float Et = fabsf(S) * 3.0517578125e-5f * 1.01f;                      // S is the floor of a 16-mantissa-bit key
+                const float Et = fabsf(S) * 3.0517578125e-5f * 1.01f;                      // slack of one key step on the upper side (S itself is a raw score, not a truncated key)
                 const float En = exact_inputs ? 0.f : (0.5f * delta * (2.f * ds + 3.f * delta) + 1.52587890625e-5f * 0.5f * (na * na + nb * nb)) * 1.01f;
                 L = fminf(L, sqrtf(2.f * fmaxf(S - En, 0.f)) * 0.999999f);
                 U = sqrtf(2.f * fmaxf(S + Et + En, 0.f)) * 1.000001f;
